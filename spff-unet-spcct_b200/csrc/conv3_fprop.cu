@@ -1,0 +1,444 @@
+// 3x3x3 convolution (stride 1, zero pad 1, no bias) as an implicit GEMM on tcgen05 — forward and input
+// gradient. Replaces the F.conv3d / convolution_backward(input) library calls behind
+// `_conv3x3xk` (reference innovative3D/models.py:616-618).
+//
+// Formulation ("kw folded into N"). Positions of one energy plane are flattened q = h*W + w. For
+// one (sample n, 128 flattened positions, block of 32 output channels) the kernel computes, for
+// every output plane d of a plane group, three partial sums
+//     T_kw[q][co] = sum_{kd,kh,ci} x[n][d+kd-1][q + (kh-1)*W][ci] * w[co][ci][kd][kh][kw]
+// as ONE GEMM tile with M = 128 positions, N = 3*32 = (kw, co), K = 9*Cin. The (kd,kh) taps are
+// whole-row shifts of the flattened index, so every A tile is a plain TMA box of a rank-4 tensor
+// map (C, H*W, D, N) whose out-of-bounds rows are zero filled (the h and d padding). The w shift is
+// applied in the epilogue:  y[q] = T_0[q-1] + T_1[q] + T_2[q+1]  (masked at w = 0 / w = W-1).
+// Compared with one GEMM per tap this reads each A tile from shared memory once for three taps
+// (N = 96 instead of 32) and an input plane tile loaded once feeds up to three output planes
+// (kd), which is what keeps L2->SM traffic under the tensor pipe's needs for 32..64 channels.
+//
+// Warp roles (192 threads, one CTA per SM, persistent over work items):
+//   warps 0-3  epilogue: TMEM -> registers (tcgen05.ld), w-shift add, bf16 pack, global store
+//   warp  4    TMA producer (one elected lane)
+//   warp  5    TMEM allocation + tcgen05.mma issue (one elected lane)
+#include "common.h"
+#include "ptx.cuh"
+
+namespace spff {
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kCoBlk = 32;            // output channels per work item
+constexpr int kN = 3 * kCoBlk;        // UMMA N: (kw, co)
+constexpr int kMaxPlanes = 5;         // output planes per group: 5 * 96 = 480 TMEM columns
+constexpr int kThreads = 192;
+
+struct FpropParams {
+  int n, d, hw, w;
+  int nkc;      // K chunks per tap (cin / KC)
+  int ncb;      // output channel blocks (cout / 32)
+  int mstep;    // output positions per tile: 128 (tile edges are row edges) or 126 (1-row halo each side)
+  int halo;     // 0 or 1
+  int qtiles;   // ceil(hw / mstep)
+  int G;        // planes per group
+  int ngroups;  // ceil(d / G)
+  long long items;
+  __nv_bfloat16* y;
+  long long ldy;
+};
+
+template <int KC>
+struct SmemLayout {
+  static constexpr int kStages = (KC == 64) ? 6 : 8;
+  static constexpr int kABytes = kTileM * KC * 2;
+  static constexpr int kWBlock = kN * KC * 2;     // one kd block: 96 rows
+  static constexpr int kWBytes = 3 * kWBlock;     // three kd blocks per (kh, kc)
+  static constexpr int kWStages = 2;
+  static constexpr int kOffA = 0;
+  static constexpr int kOffW = kOffA + kStages * kABytes;
+  static constexpr int kOffX = kOffW + kWStages * kWBytes;          // epilogue exchange rows
+  static constexpr int kXBytes = 2 * 4 * 2 * kCoBlk * 4;
+  static constexpr int kOffBar = kOffX + kXBytes;
+  static constexpr int kNumBars = 2 * kStages + 2 * kWStages + 2;
+  static constexpr int kOffTmem = kOffBar + kNumBars * 8;
+  static constexpr int kTotal = kOffTmem + 16;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                   const FpropParams p) {
+  using L = SmemLayout<KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzled tiles need 1024 B alignment
+  uint8_t* sA = smem + L::kOffA;
+  uint8_t* sW = smem + L::kOffW;
+  float* sX = reinterpret_cast<float*>(smem + L::kOffX);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + L::kStages;
+  uint64_t* wfull = bars + 2 * L::kStages;
+  uint64_t* wempty = wfull + L::kWStages;
+  uint64_t* acc_full = wempty + L::kWStages;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < L::kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < L::kWStages; ++i) {
+      mbar_init(&wfull[i], 1);
+      mbar_init(&wempty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  constexpr uint32_t kSwz = (KC == 64) ? kSwizzle128 : kSwizzle64;
+  constexpr uint32_t kSbo = (KC == 64) ? 1024 : 512;
+  const uint64_t desc_hi = make_smem_desc_hi(16, kSbo, kSwz);
+  const uint32_t idesc = make_idesc_bf16(kTileM, kN, 0, 0);
+
+  auto decode = [&](long long item, int& n, int& qt, int& pg, int& cb) {
+    cb = static_cast<int>(item % p.ncb);
+    long long r = item / p.ncb;
+    pg = static_cast<int>(r % p.ngroups);
+    r /= p.ngroups;
+    qt = static_cast<int>(r % p.qtiles);
+    n = static_cast<int>(r / p.qtiles);
+  };
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0, ws = 0;
+      uint32_t ph = 0, wph = 0;
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int n, qt, pg, cb;
+        decode(item, n, qt, pg, cb);
+        const int tq0 = qt * p.mstep - p.halo;
+        const int d0 = pg * p.G;
+        const int dlo = max(0, d0 - 1);
+        const int dhi = min(p.d - 1, d0 + p.G);
+        for (int kh = 0; kh < 3; ++kh) {
+          for (int kc = 0; kc < p.nkc; ++kc) {
+            mbar_wait(&wempty[ws], wph ^ 1);
+            mbar_expect_tx(&wfull[ws], L::kWBytes);
+            const int wrow = ((cb * 3 + kh) * p.nkc + kc) * 3 * kN;
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd)
+              tma_load_2d(sW + ws * L::kWBytes + kd * L::kWBlock, &tmap_w, &wfull[ws], 0, wrow + kd * kN);
+            if (++ws == L::kWStages) {
+              ws = 0;
+              wph ^= 1;
+            }
+            for (int dp = dlo; dp <= dhi; ++dp) {
+              mbar_wait(&empty[s], ph ^ 1);
+              mbar_expect_tx(&full[s], L::kABytes);
+              tma_load_4d(sA + s * L::kABytes, &tmap_x, &full[s], kc * KC, tq0 + (kh - 1) * p.w, dp, n);
+              if (++s == L::kStages) {
+                s = 0;
+                ph ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int s = 0, ws = 0;
+      uint32_t ph = 0, wph = 0, aph = 0;
+      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+        int n, qt, pg, cb;
+        decode(item, n, qt, pg, cb);
+        const int d0 = pg * p.G;
+        const int dlo = max(0, d0 - 1);
+        const int dhi = min(p.d - 1, d0 + p.G);
+        const int dend = min(p.d, d0 + p.G);
+        mbar_wait(acc_empty, aph ^ 1);
+        tc_fence_after();
+        uint32_t touched = 0;
+        for (int kh = 0; kh < 3; ++kh) {
+          for (int kc = 0; kc < p.nkc; ++kc) {
+            mbar_wait(&wfull[ws], wph);
+            const uint32_t wbase = smem_u32(sW + ws * L::kWBytes);
+            for (int dp = dlo; dp <= dhi; ++dp) {
+              mbar_wait(&full[s], ph);
+              tc_fence_after();
+              const uint32_t abase = smem_u32(sA + s * L::kABytes);
+#pragma unroll
+              for (int kd = 0; kd < 3; ++kd) {
+                const int dout = dp - (kd - 1);
+                if (dout >= d0 && dout < dend) {
+                  const int j = dout - d0;
+                  const uint32_t dcol = tmem_base + j * kN;
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k) {
+                    const uint64_t ad = smem_desc(desc_hi, abase + k * 32);
+                    const uint64_t bd = smem_desc(desc_hi, wbase + kd * L::kWBlock + k * 32);
+                    umma_bf16(dcol, ad, bd, idesc, ((touched >> j) & 1u) | (k > 0 ? 1u : 0u));
+                  }
+                  touched |= 1u << j;
+                }
+              }
+              umma_commit(&empty[s]);
+              if (++s == L::kStages) {
+                s = 0;
+                ph ^= 1;
+              }
+            }
+            umma_commit(&wempty[ws]);
+            if (++ws == L::kWStages) {
+              ws = 0;
+              wph ^= 1;
+            }
+          }
+        }
+        umma_commit(acc_full);
+        aph ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3)
+    uint32_t aph = 0;
+    uint32_t xpar = 0;
+    const int m = warp * 32 + lane;  // tile row == TMEM lane
+    for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int n, qt, pg, cb;
+      decode(item, n, qt, pg, cb);
+      const int tq0 = qt * p.mstep - p.halo;
+      const int d0 = pg * p.G;
+      const int dend = min(p.d, d0 + p.G);
+      const int q = tq0 + m;
+      const int wq = (q >= 0) ? (q % p.w) : 0;
+      const bool row_out = (m >= p.halo) && (m < p.halo + p.mstep) && (q < p.hw);
+      const bool has_left = wq != 0;
+      const bool has_right = wq != p.w - 1;
+      mbar_wait(acc_full, aph);
+      aph ^= 1;
+      tc_fence_after();
+      for (int d = d0; d < dend; ++d) {
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (d - d0) * kN;
+        uint32_t t0[32], t1[32], t2[32];
+        tmem_ld_32x32(tcol, t0);
+        tmem_ld_32x32(tcol + 32, t1);
+        tmem_ld_32x32(tcol + 64, t2);
+        tmem_ld_wait();
+        float* xrow = sX + (xpar * 4 + warp) * 2 * kCoBlk;
+        if (lane == 31) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) xrow[c] = __uint_as_float(t0[c]);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) xrow[kCoBlk + c] = __uint_as_float(t2[c]);
+        }
+        named_bar_sync(1, 128);
+        const float* left = sX + (xpar * 4 + (warp > 0 ? warp - 1 : 0)) * 2 * kCoBlk;             // T0 of row m-1
+        const float* right = sX + (xpar * 4 + (warp < 3 ? warp + 1 : 3)) * 2 * kCoBlk + kCoBlk;  // T2 of row m+1
+        uint32_t packed[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float acc2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float a = __uint_as_float(t0[c + e]);
+            float b = __uint_as_float(t2[c + e]);
+            float l = __shfl_up_sync(0xffffffffu, a, 1);
+            float r = __shfl_down_sync(0xffffffffu, b, 1);
+            if (lane == 0) l = left[c + e];
+            if (lane == 31) r = right[c + e];
+            float v = __uint_as_float(t1[c + e]);
+            if (has_left) v += l;
+            if (has_right) v += r;
+            acc2[e] = v;
+          }
+          packed[c >> 1] = pack_bf16x2(acc2[0], acc2[1]);
+        }
+        if (row_out) {
+          __nv_bfloat16* dst = p.y + ((static_cast<long long>(n) * p.d + d) * p.hw + q) * p.ldy + cb * kCoBlk;
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            d4[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        }
+        xpar ^= 1;
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int KC>
+int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y, long long ldy, int cout,
+                 spff_shape s, cudaStream_t stream) {
+  using L = SmemLayout<KC>;
+  FpropParams p;
+  p.n = s.n;
+  p.d = s.d;
+  p.hw = s.h * s.w;
+  p.w = s.w;
+  p.nkc = cin / KC;
+  p.ncb = cout / kCoBlk;
+  if (kTileM % s.w == 0) {
+    p.mstep = 128;
+    p.halo = 0;
+  } else {
+    p.mstep = 126;
+    p.halo = 1;
+  }
+  p.qtiles = (p.hw + p.mstep - 1) / p.mstep;
+  p.G = s.d < kMaxPlanes ? s.d : kMaxPlanes;
+  p.ngroups = (s.d + p.G - 1) / p.G;
+  p.items = static_cast<long long>(s.n) * p.qtiles * p.ngroups * p.ncb;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.ldy = ldy;
+
+  CUtensorMap tx, tw;
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(p.hw), static_cast<uint64_t>(s.d),
+                        static_cast<uint64_t>(s.n)};
+    uint64_t str[3] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(ldx) * 2 * p.hw,
+                       static_cast<uint64_t>(ldx) * 2 * p.hw * s.d};
+    uint32_t box[4] = {KC, kTileM, 1, 1};
+    int e = encode_tmap_bf16(&tx, x, 4, dims, str, box, KC * 2);
+    if (e) return e;
+  }
+  {
+    const uint64_t rows = static_cast<uint64_t>(p.ncb) * 3 * p.nkc * 3 * kN;
+    uint64_t dims[2] = {KC, rows};
+    uint64_t str[1] = {KC * 2};
+    uint32_t box[2] = {KC, kN};
+    int e = encode_tmap_bf16(&tw, wpk, 2, dims, str, box, KC * 2);
+    if (e) return e;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPFF_CUDA(cudaFuncSetAttribute(conv3_fprop_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   L::kTotal + 1024));
+    attr_set = true;
+  }
+  int ctas = debug_ctas() > 0 ? debug_ctas() : num_sms();
+  if (p.items < ctas) ctas = static_cast<int>(p.items);
+  conv3_fprop_kernel<KC><<<ctas, kThreads, L::kTotal + 1024, stream>>>(tx, tw, p);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing: nn.Conv3d weight [Cout][Cin][3][3][3] fp32 -> bf16 GEMM operand
+//   P[cb][kh][kc][kd][kw][co32][KC],  value = w[cb*32+co][kc*KC+k][kd][kh][kw]          (forward)
+//   P[cb][kh][kc][kd][kw][ci32][KC],  value = w[kc*KC+k][cb*32+ci][2-kd][2-kh][2-kw]    (dgrad)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_conv3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
+                                         int cin, int KC, int dgrad) {
+  const int gout = dgrad ? cin : cout;  // GEMM N channels
+  const int gin = dgrad ? cout : cin;   // GEMM K channels
+  const int nkc = gin / KC;
+  const long long total = static_cast<long long>(gout) * gin * 27;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int k = static_cast<int>(r % KC);
+    r /= KC;
+    const int co = static_cast<int>(r % kCoBlk);
+    r /= kCoBlk;
+    const int kw = static_cast<int>(r % 3);
+    r /= 3;
+    const int kd = static_cast<int>(r % 3);
+    r /= 3;
+    const int kc = static_cast<int>(r % nkc);
+    r /= nkc;
+    const int kh = static_cast<int>(r % 3);
+    r /= 3;
+    const int cb = static_cast<int>(r);
+    const int go = cb * kCoBlk + co;
+    const int gi = kc * KC + k;
+    float v;
+    if (!dgrad)
+      v = w[((static_cast<long long>(go) * cin + gi) * 3 + kd) * 9 + kh * 3 + kw];
+    else
+      v = w[((static_cast<long long>(gi) * cin + go) * 3 + (2 - kd)) * 9 + (2 - kh) * 3 + (2 - kw)];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace
+
+int conv3_kc(int gemm_k_channels) { return (gemm_k_channels % 64 == 0) ? 64 : 32; }
+
+}  // namespace spff
+
+extern "C" {
+
+int spff_pack_conv3_weight(const float* w, void* w_fwd, void* w_dgrad, int cout, int cin, void* stream) {
+  SPFF_REQUIRE(cout % 32 == 0 && cin % 32 == 0, "pack_conv3_weight: cin %d / cout %d must be multiples of 32", cin,
+               cout);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(cout) * cin * 27;
+  const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  if (w_fwd)
+    spff::pack_conv3_weight_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_fwd), cout, cin,
+                                                           spff::conv3_kc(cin), 0);
+  if (w_dgrad)
+    spff::pack_conv3_weight_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_dgrad), cout, cin,
+                                                           spff::conv3_kc(cout), 1);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int conv3_common(const void* x, long long ldx, int cin, const void* wpk, void* y, long long ldy, int cout,
+                        spff_shape s, void* stream, const char* who) {
+  int e = spff_device_check();
+  if (e) return e;
+  SPFF_REQUIRE(x && wpk && y, "%s: null pointer", who);
+  SPFF_REQUIRE(cin % 32 == 0 && cout % 32 == 0 && cin > 0 && cout > 0, "%s: channels (%d -> %d) must be multiples of 32",
+               who, cin, cout);
+  SPFF_REQUIRE(ldx >= cin && ldy >= cout && ldx % 8 == 0 && ldy % 8 == 0, "%s: bad channel pitch %lld / %lld", who, ldx,
+               ldy);
+  SPFF_REQUIRE(s.n > 0 && s.d > 0 && s.h > 0 && s.w > 0, "%s: empty shape", who);
+  SPFF_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(wpk) & 15) == 0,
+               "%s: pointers must be 16-byte aligned", who);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (spff::conv3_kc(cin) == 64) return spff::launch_fprop<64>(x, ldx, cin, wpk, y, ldy, cout, s, st);
+  return spff::launch_fprop<32>(x, ldx, cin, wpk, y, ldy, cout, s, st);
+}
+
+int spff_conv3d_k3_fwd(const void* x, long long ldx, int cin, const void* w_fwd, void* y, long long ldy, int cout,
+                       spff_shape s, void* stream) {
+  return conv3_common(x, ldx, cin, w_fwd, y, ldy, cout, s, stream, "conv3d_k3_fwd");
+}
+
+int spff_conv3d_k3_dgrad(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
+                         int cin, spff_shape s, void* stream) {
+  return conv3_common(dy, lddy, cout, w_dgrad, dx, lddx, cin, s, stream, "conv3d_k3_dgrad");
+}
+
+}  // extern "C"

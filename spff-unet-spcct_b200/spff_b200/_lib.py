@@ -1,0 +1,86 @@
+"""ctypes binding of libspff_b200.so (C ABI: include/spff_b200.h).
+
+The library is the product: there is no Python/PyTorch fallback behind these calls. Loading fails
+loudly when the shared object is missing, and every compute entry point returns
+SPFF_ERR_UNSUPPORTED_ARCH (raised here as RuntimeError) on anything that is not an sm_100 GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspff_b200.so")
+
+
+class Shape(Structure):
+    """spff_shape: samples, energy bins (depth), height, width."""
+
+    _fields_ = [("n", c_int), ("d", c_int), ("h", c_int), ("w", c_int)]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C spff-unet-spcct_b200/csrc`). spff_b200 has no fallback path."
+        )
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+lib.spff_last_error.restype = c_char_p
+lib.spff_version.restype = c_int
+
+_P = c_void_p
+_LL = c_longlong
+
+# name -> argtypes, exactly the prototypes of include/spff_b200.h (restype int unless noted)
+_PROTOTYPES = {
+    "spff_device_check": [],
+    "spff_debug_set": [c_int, _LL],
+    "spff_pack_conv3_weight": [_P, _P, _P, c_int, c_int, _P],
+    "spff_conv3d_k3_fwd": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P],
+    "spff_conv3d_k3_dgrad": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P],
+}
+
+_SIZE_T_FUNCS = set()
+
+
+def _declare():
+    for name, argtypes in _PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_size_t if name in _SIZE_T_FUNCS else c_int
+
+
+_declare()
+
+
+def exported_symbols():
+    """Names this binding expects the shared object to export (checked by the CPU tests)."""
+    return ["spff_version", "spff_last_error"] + list(_PROTOTYPES)
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib.spff_last_error()
+        raise RuntimeError(f"libspff_b200 {what} failed ({code}): {msg.decode() if msg else ''}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib, name)(*args), name)
+
+
+def ptr(t) -> c_void_p:
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> c_void_p:
+    import torch
+
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,98 @@
+"""GPU parity of the tcgen05 3x3x3 convolution (forward / input gradient / weight gradient) against
+F.conv3d — the call the reference makes at innovative3D/models.py:616-618 — on bf16-rounded inputs.
+Tolerance: outputs are stored in bf16 (8 bit mantissa) from fp32 accumulators, so the bound is
+rel-L2 <= 4e-3 and max-abs <= 2^-7 * max|y| (one bf16 ulp of the largest value)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(n, c, d, h, w, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(n, c, d, h, w, generator=g).cuda()
+
+
+def _to_ndhwc_bf16(x, ld=None):
+    n, c, d, h, w = x.shape
+    ld = ld or c
+    buf = torch.zeros(n, d, h, w, ld, dtype=torch.bfloat16, device=x.device)
+    buf[..., :c] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    return buf
+
+
+def _from_ndhwc(buf, c):
+    return buf[..., :c].permute(0, 4, 1, 2, 3).float()
+
+
+CASES = [
+    # n, d, h, w, cin, cout
+    (2, 5, 16, 16, 32, 32),
+    (1, 5, 8, 8, 32, 64),
+    (2, 5, 16, 16, 64, 32),
+    (1, 5, 16, 16, 64, 64),
+    (1, 5, 8, 8, 128, 64),
+    (1, 5, 16, 24, 32, 32),   # W does not divide 128: halo tiles (mstep 126)
+    (1, 3, 4, 8, 64, 128),
+    (1, 7, 8, 8, 32, 32),     # two plane groups
+    (3, 5, 32, 32, 32, 32),
+    (1, 5, 4, 4, 256, 256),
+]
+
+
+@pytest.mark.parametrize("n,d,h,w,cin,cout", CASES)
+def test_conv3_fwd(n, d, h, w, cin, cout):
+    from spff_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    x = _mk(n, cin, d, h, w, 1)
+    wt = _mk(cout, cin, 3, 3, 3, 2)[..., 0:3, 0:3, 0:3].contiguous() * (1.0 / (27 * cin) ** 0.5)
+    xb = _to_ndhwc_bf16(x)
+    wf, _ = ops.pack_conv3_weight(wt)
+    y = torch.full((n, d, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.conv3d_k3_fwd(xb, cin, wf, y, cout)
+    torch.cuda.synchronize()
+    ref = F.conv3d(xb.float().permute(0, 4, 1, 2, 3), wt.to(torch.bfloat16).float(), padding=1)
+    got = _from_ndhwc(y, cout)
+    assert torch.isfinite(got).all()
+    rel = (got - ref).norm() / ref.norm()
+    assert rel < 4e-3, rel
+    assert (got - ref).abs().max() <= ref.abs().max() * 2 ** -7
+
+
+@pytest.mark.parametrize("n,d,h,w,cin,cout", CASES[:7])
+def test_conv3_dgrad(n, d, h, w, cin, cout):
+    from spff_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    dy = _mk(n, cout, d, h, w, 3)
+    wt = _mk(cout, cin, 3, 3, 3, 4).contiguous() * (1.0 / (27 * cout) ** 0.5)
+    dyb = _to_ndhwc_bf16(dy)
+    _, wd = ops.pack_conv3_weight(wt)
+    dx = torch.full((n, d, h, w, cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.conv3d_k3_dgrad(dyb, cout, wd, dx, cin)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose3d(dyb.float().permute(0, 4, 1, 2, 3), wt.to(torch.bfloat16).float(), padding=1)
+    got = _from_ndhwc(dx, cin)
+    rel = (got - ref).norm() / ref.norm()
+    assert rel < 4e-3, rel
+
+
+def test_conv3_fwd_strided_views():
+    """Input read from / output written into channel slices of wider buffers (the skip-concat case)."""
+    from spff_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    n, d, h, w, cin, cout = 1, 5, 16, 16, 64, 32
+    x = _mk(n, cin, d, h, w, 5)
+    wt = _mk(cout, cin, 3, 3, 3, 6).contiguous() * 0.05
+    xb = _to_ndhwc_bf16(x, ld=96)
+    wf, _ = ops.pack_conv3_weight(wt)
+    y = torch.zeros(n, d, h, w, 64, dtype=torch.bfloat16, device="cuda")
+    ops.conv3d_k3_fwd(xb, cin, wf, y[..., 32:], cout)
+    torch.cuda.synchronize()
+    ref = F.conv3d(xb[..., :cin].float().permute(0, 4, 1, 2, 3), wt.to(torch.bfloat16).float(), padding=1)
+    got = _from_ndhwc(y[..., 32:], cout)
+    assert (y[..., :32] == 0).all()
+    assert (got - ref).norm() / ref.norm() < 4e-3
