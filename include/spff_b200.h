@@ -70,6 +70,14 @@ int spff_conv3d_k3_fwd(const void* x, long long ldx, int cin, const void* w_fwd,
 int spff_conv3d_k3_dgrad(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
                          int cin, spff_shape s, void* stream);
 
+/* dw[cout][cin][3][3][3] (fp32) = beta*dw + weight gradient (ATen convolution_backward, grad_weight).
+ * Split over positions; fp32 partial tiles go to `workspace` (size from the query below, which
+ * depends on the SM count of the current device) and are reduced in a fixed order. */
+size_t spff_conv3d_k3_wgrad_workspace(int cin, int cout, spff_shape s);
+int spff_conv3d_k3_wgrad(const void* x, long long ldx, int cin, const void* dy, long long lddy, int cout,
+                         spff_shape s, float* dw, float beta, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* @@ENTRY_POINTS@@ */
 
 #ifdef __cplusplus

@@ -45,28 +45,34 @@ struct FpropParams {
   long long ldy;
 };
 
-template <int KC>
+template <int KC, bool RES>
 struct SmemLayout {
   static constexpr int kStages = (KC == 64) ? 6 : 8;
   static constexpr int kABytes = kTileM * KC * 2;
   static constexpr int kWBlock = kN * KC * 2;     // one kd block: 96 rows
   static constexpr int kWBytes = 3 * kWBlock;     // three kd blocks per (kh, kc)
-  static constexpr int kWStages = 2;
+  // RES: all 27 taps of one 32-channel output block stay in smem (cin <= 64 -> one K chunk per tap);
+  // otherwise the (kh, kc) weight blocks stream through a 2-deep ring.
+  static constexpr int kWStages = RES ? 3 : 2;
   static constexpr int kOffA = 0;
   static constexpr int kOffW = kOffA + kStages * kABytes;
   static constexpr int kOffX = kOffW + kWStages * kWBytes;          // epilogue exchange rows
   static constexpr int kXBytes = 2 * 4 * 2 * kCoBlk * 4;
   static constexpr int kOffBar = kOffX + kXBytes;
-  static constexpr int kNumBars = 2 * kStages + 2 * kWStages + 2;
+  static constexpr int kNumBars = 2 * kStages + 2 * 3 + 2 * kMaxPlanes;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmem + 16;
 };
 
-template <int KC>
+// Loop order. Streamed weights (RES = false): kh -> kc -> input plane; every output plane of the
+// group completes at the end of the item. Resident weights (RES = true): input plane -> kh; output
+// plane j is complete once input plane j+1 is consumed, so its epilogue overlaps the MMAs of the
+// following planes and of the next item (per-plane full/empty barriers on the TMEM accumulators).
+template <int KC, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const FpropParams p) {
-  using L = SmemLayout<KC>;
+  using L = SmemLayout<KC, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzled tiles need 1024 B alignment
   uint8_t* sA = smem + L::kOffA;
@@ -76,9 +82,9 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint64_t* full = bars;
   uint64_t* empty = bars + L::kStages;
   uint64_t* wfull = bars + 2 * L::kStages;
-  uint64_t* wempty = wfull + L::kWStages;
-  uint64_t* acc_full = wempty + L::kWStages;
-  uint64_t* acc_empty = acc_full + 1;
+  uint64_t* wempty = wfull + 3;
+  uint64_t* acc_full = wempty + 3;
+  uint64_t* acc_empty = acc_full + kMaxPlanes;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -89,12 +95,14 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < L::kWStages; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&wfull[i], 1);
       mbar_init(&wempty[i], 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 128);
+    for (int i = 0; i < kMaxPlanes; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 4 && lane == 0) {
@@ -115,9 +123,18 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   const uint64_t desc_hi = make_smem_desc_hi(16, kSbo, kSwz);
   const uint32_t idesc = make_idesc_bf16(kTileM, kN, 0, 0);
 
+  // RES: a CTA keeps one output-channel block (cb = blockIdx % ncb) and strides over positions.
+  const long long item0 = RES ? (blockIdx.x / p.ncb) : blockIdx.x;
+  const long long istep = RES ? (gridDim.x / p.ncb) : gridDim.x;
+  const long long nitems = RES ? p.items / p.ncb : p.items;
   auto decode = [&](long long item, int& n, int& qt, int& pg, int& cb) {
-    cb = static_cast<int>(item % p.ncb);
-    long long r = item / p.ncb;
+    long long r = item;
+    if (RES) {
+      cb = blockIdx.x % p.ncb;
+    } else {
+      cb = static_cast<int>(r % p.ncb);
+      r /= p.ncb;
+    }
     pg = static_cast<int>(r % p.ngroups);
     r /= p.ngroups;
     qt = static_cast<int>(r % p.qtiles);
@@ -129,32 +146,56 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     if (lane == 0) {
       int s = 0, ws = 0;
       uint32_t ph = 0, wph = 0;
-      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+      if (RES) {
+        const int cb = blockIdx.x % p.ncb;
+        for (int kh = 0; kh < 3; ++kh) {
+          mbar_expect_tx(&wfull[kh], L::kWBytes);
+          const int wrow = (cb * 3 + kh) * 3 * kN;
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd)
+            tma_load_2d(sW + kh * L::kWBytes + kd * L::kWBlock, &tmap_w, &wfull[kh], 0, wrow + kd * kN);
+        }
+      }
+      for (long long item = item0; item < nitems; item += istep) {
         int n, qt, pg, cb;
         decode(item, n, qt, pg, cb);
         const int tq0 = qt * p.mstep - p.halo;
         const int d0 = pg * p.G;
         const int dlo = max(0, d0 - 1);
         const int dhi = min(p.d - 1, d0 + p.G);
-        for (int kh = 0; kh < 3; ++kh) {
-          for (int kc = 0; kc < p.nkc; ++kc) {
-            mbar_wait(&wempty[ws], wph ^ 1);
-            mbar_expect_tx(&wfull[ws], L::kWBytes);
-            const int wrow = ((cb * 3 + kh) * p.nkc + kc) * 3 * kN;
-#pragma unroll
-            for (int kd = 0; kd < 3; ++kd)
-              tma_load_2d(sW + ws * L::kWBytes + kd * L::kWBlock, &tmap_w, &wfull[ws], 0, wrow + kd * kN);
-            if (++ws == L::kWStages) {
-              ws = 0;
-              wph ^= 1;
-            }
-            for (int dp = dlo; dp <= dhi; ++dp) {
+        if (RES) {
+          for (int dp = dlo; dp <= dhi; ++dp) {
+            for (int kh = 0; kh < 3; ++kh) {
               mbar_wait(&empty[s], ph ^ 1);
               mbar_expect_tx(&full[s], L::kABytes);
-              tma_load_4d(sA + s * L::kABytes, &tmap_x, &full[s], kc * KC, tq0 + (kh - 1) * p.w, dp, n);
+              tma_load_4d(sA + s * L::kABytes, &tmap_x, &full[s], 0, tq0 + (kh - 1) * p.w, dp, n);
               if (++s == L::kStages) {
                 s = 0;
                 ph ^= 1;
+              }
+            }
+          }
+        } else {
+          for (int kh = 0; kh < 3; ++kh) {
+            for (int kc = 0; kc < p.nkc; ++kc) {
+              mbar_wait(&wempty[ws], wph ^ 1);
+              mbar_expect_tx(&wfull[ws], L::kWBytes);
+              const int wrow = ((cb * 3 + kh) * p.nkc + kc) * 3 * kN;
+#pragma unroll
+              for (int kd = 0; kd < 3; ++kd)
+                tma_load_2d(sW + ws * L::kWBytes + kd * L::kWBlock, &tmap_w, &wfull[ws], 0, wrow + kd * kN);
+              if (++ws == L::kWStages) {
+                ws = 0;
+                wph ^= 1;
+              }
+              for (int dp = dlo; dp <= dhi; ++dp) {
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], L::kABytes);
+                tma_load_4d(sA + s * L::kABytes, &tmap_x, &full[s], kc * KC, tq0 + (kh - 1) * p.w, dp, n);
+                if (++s == L::kStages) {
+                  s = 0;
+                  ph ^= 1;
+                }
               }
             }
           }
@@ -165,63 +206,90 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       int s = 0, ws = 0;
-      uint32_t ph = 0, wph = 0, aph = 0;
-      for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+      uint32_t ph = 0, wph = 0;
+      uint32_t accpar = 0;  // per accumulator slot: parity of its next acc_empty wait
+      if (RES) {
+        for (int kh = 0; kh < 3; ++kh) mbar_wait(&wfull[kh], 0);
+      }
+      // one A stage against the kd blocks at wbase; returns the updated touched mask
+      auto stage_mmas = [&](uint32_t abase, uint32_t wbase, int dp, int d0, int dend, uint32_t touched) -> uint32_t {
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+          const int dout = dp - (kd - 1);
+          if (dout >= d0 && dout < dend) {
+            const int j = dout - d0;
+            if (!((touched >> j) & 1u)) {  // first MMA into this accumulator: the epilogue must have drained it
+              mbar_wait(&acc_empty[j], ((accpar >> j) & 1u) ^ 1u);
+              accpar ^= 1u << j;
+              tc_fence_after();
+            }
+            const uint32_t dcol = tmem_base + j * kN;
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              const uint64_t ad = smem_desc(desc_hi, abase + k * 32);
+              const uint64_t bd = smem_desc(desc_hi, wbase + kd * L::kWBlock + k * 32);
+              umma_bf16(dcol, ad, bd, idesc, ((touched >> j) & 1u) | (k > 0 ? 1u : 0u));
+            }
+            touched |= 1u << j;
+          }
+        }
+        return touched;
+      };
+      for (long long item = item0; item < nitems; item += istep) {
         int n, qt, pg, cb;
         decode(item, n, qt, pg, cb);
         const int d0 = pg * p.G;
         const int dlo = max(0, d0 - 1);
         const int dhi = min(p.d - 1, d0 + p.G);
         const int dend = min(p.d, d0 + p.G);
-        mbar_wait(acc_empty, aph ^ 1);
-        tc_fence_after();
         uint32_t touched = 0;
-        for (int kh = 0; kh < 3; ++kh) {
-          for (int kc = 0; kc < p.nkc; ++kc) {
-            mbar_wait(&wfull[ws], wph);
-            const uint32_t wbase = smem_u32(sW + ws * L::kWBytes);
-            for (int dp = dlo; dp <= dhi; ++dp) {
+        if (RES) {
+          for (int dp = dlo; dp <= dhi; ++dp) {
+            for (int kh = 0; kh < 3; ++kh) {
               mbar_wait(&full[s], ph);
               tc_fence_after();
-              const uint32_t abase = smem_u32(sA + s * L::kABytes);
-#pragma unroll
-              for (int kd = 0; kd < 3; ++kd) {
-                const int dout = dp - (kd - 1);
-                if (dout >= d0 && dout < dend) {
-                  const int j = dout - d0;
-                  const uint32_t dcol = tmem_base + j * kN;
-#pragma unroll
-                  for (int k = 0; k < KC / 16; ++k) {
-                    const uint64_t ad = smem_desc(desc_hi, abase + k * 32);
-                    const uint64_t bd = smem_desc(desc_hi, wbase + kd * L::kWBlock + k * 32);
-                    umma_bf16(dcol, ad, bd, idesc, ((touched >> j) & 1u) | (k > 0 ? 1u : 0u));
-                  }
-                  touched |= 1u << j;
-                }
-              }
+              touched = stage_mmas(smem_u32(sA + s * L::kABytes), smem_u32(sW + kh * L::kWBytes), dp, d0, dend, touched);
               umma_commit(&empty[s]);
               if (++s == L::kStages) {
                 s = 0;
                 ph ^= 1;
               }
             }
-            umma_commit(&wempty[ws]);
-            if (++ws == L::kWStages) {
-              ws = 0;
-              wph ^= 1;
+            if (dp - 1 >= d0 && dp - 1 < dend) umma_commit(&acc_full[dp - 1 - d0]);
+            if (dp == dhi && dhi < dend) umma_commit(&acc_full[dhi - d0]);
+          }
+        } else {
+          for (int kh = 0; kh < 3; ++kh) {
+            for (int kc = 0; kc < p.nkc; ++kc) {
+              mbar_wait(&wfull[ws], wph);
+              const uint32_t wbase = smem_u32(sW + ws * L::kWBytes);
+              for (int dp = dlo; dp <= dhi; ++dp) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                touched = stage_mmas(smem_u32(sA + s * L::kABytes), wbase, dp, d0, dend, touched);
+                umma_commit(&empty[s]);
+                if (++s == L::kStages) {
+                  s = 0;
+                  ph ^= 1;
+                }
+              }
+              umma_commit(&wempty[ws]);
+              if (++ws == L::kWStages) {
+                ws = 0;
+                wph ^= 1;
+              }
             }
           }
+          for (int j = 0; j < dend - d0; ++j) umma_commit(&acc_full[j]);
         }
-        umma_commit(acc_full);
-        aph ^= 1;
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 0-3)
-    uint32_t aph = 0;
+    uint32_t accpar = 0;  // per accumulator slot: parity of its next acc_full wait
     uint32_t xpar = 0;
     const int m = warp * 32 + lane;  // tile row == TMEM lane
-    for (long long item = blockIdx.x; item < p.items; item += gridDim.x) {
+    for (long long item = item0; item < nitems; item += istep) {
       int n, qt, pg, cb;
       decode(item, n, qt, pg, cb);
       const int tq0 = qt * p.mstep - p.halo;
@@ -232,46 +300,56 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       const bool row_out = (m >= p.halo) && (m < p.halo + p.mstep) && (q < p.hw);
       const bool has_left = wq != 0;
       const bool has_right = wq != p.w - 1;
-      mbar_wait(acc_full, aph);
-      aph ^= 1;
-      tc_fence_after();
       for (int d = d0; d < dend; ++d) {
-        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (d - d0) * kN;
+        const int j = d - d0;
+        mbar_wait(&acc_full[j], (accpar >> j) & 1u);
+        accpar ^= 1u << j;
+        tc_fence_after();
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + j * kN;
         uint32_t t0[32], t1[32], t2[32];
         tmem_ld_32x32(tcol, t0);
         tmem_ld_32x32(tcol + 32, t1);
         tmem_ld_32x32(tcol + 64, t2);
         tmem_ld_wait();
-        float* xrow = sX + (xpar * 4 + warp) * 2 * kCoBlk;
+        tc_fence_before();
+        mbar_arrive(&acc_empty[j]);  // accumulator is in registers: the next item may overwrite it
+        // rows m-1 / m+1 live in the neighbouring lanes; across warps they go through smem
+        float4* xrow = reinterpret_cast<float4*>(sX + (xpar * 4 + warp) * 2 * kCoBlk);
         if (lane == 31) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) xrow[c] = __uint_as_float(t0[c]);
+          for (int v = 0; v < 8; ++v)
+            xrow[v] = make_float4(__uint_as_float(t0[4 * v]), __uint_as_float(t0[4 * v + 1]),
+                                  __uint_as_float(t0[4 * v + 2]), __uint_as_float(t0[4 * v + 3]));
         }
         if (lane == 0) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) xrow[kCoBlk + c] = __uint_as_float(t2[c]);
+          for (int v = 0; v < 8; ++v)
+            xrow[8 + v] = make_float4(__uint_as_float(t2[4 * v]), __uint_as_float(t2[4 * v + 1]),
+                                      __uint_as_float(t2[4 * v + 2]), __uint_as_float(t2[4 * v + 3]));
         }
         named_bar_sync(1, 128);
-        const float* left = sX + (xpar * 4 + (warp > 0 ? warp - 1 : 0)) * 2 * kCoBlk;             // T0 of row m-1
-        const float* right = sX + (xpar * 4 + (warp < 3 ? warp + 1 : 3)) * 2 * kCoBlk + kCoBlk;  // T2 of row m+1
+        const float4* lrow = reinterpret_cast<const float4*>(sX + (xpar * 4 + (warp > 0 ? warp - 1 : 0)) * 2 * kCoBlk);
+        const float4* rrow =
+            reinterpret_cast<const float4*>(sX + (xpar * 4 + (warp < 3 ? warp + 1 : 3)) * 2 * kCoBlk + kCoBlk);
         uint32_t packed[16];
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float acc2[2];
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 lb4 = lrow[c4];  // broadcast loads, used by lane 0 / lane 31 only
+          const float4 rb4 = rrow[c4];
+          const float lb[4] = {lb4.x, lb4.y, lb4.z, lb4.w};
+          const float rb[4] = {rb4.x, rb4.y, rb4.z, rb4.w};
+          float v[4];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            float a = __uint_as_float(t0[c + e]);
-            float b = __uint_as_float(t2[c + e]);
-            float l = __shfl_up_sync(0xffffffffu, a, 1);
-            float r = __shfl_down_sync(0xffffffffu, b, 1);
-            if (lane == 0) l = left[c + e];
-            if (lane == 31) r = right[c + e];
-            float v = __uint_as_float(t1[c + e]);
-            if (has_left) v += l;
-            if (has_right) v += r;
-            acc2[e] = v;
+          for (int e = 0; e < 4; ++e) {
+            const int c = 4 * c4 + e;
+            float l = __shfl_up_sync(0xffffffffu, __uint_as_float(t0[c]), 1);
+            float r = __shfl_down_sync(0xffffffffu, __uint_as_float(t2[c]), 1);
+            l = (lane == 0) ? lb[e] : l;
+            r = (lane == 31) ? rb[e] : r;
+            v[e] = __uint_as_float(t1[c]) + (has_left ? l : 0.f) + (has_right ? r : 0.f);
           }
-          packed[c >> 1] = pack_bf16x2(acc2[0], acc2[1]);
+          packed[2 * c4] = pack_bf16x2(v[0], v[1]);
+          packed[2 * c4 + 1] = pack_bf16x2(v[2], v[3]);
         }
         if (row_out) {
           __nv_bfloat16* dst = p.y + ((static_cast<long long>(n) * p.d + d) * p.hw + q) * p.ldy + cb * kCoBlk;
@@ -282,8 +360,6 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         }
         xpar ^= 1;
       }
-      tc_fence_before();
-      mbar_arrive(acc_empty);
     }
   }
 
@@ -295,10 +371,10 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   }
 }
 
-template <int KC>
+template <int KC, bool RES>
 int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y, long long ldy, int cout,
                  spff_shape s, cudaStream_t stream) {
-  using L = SmemLayout<KC>;
+  using L = SmemLayout<KC, RES>;
   FpropParams p;
   p.n = s.n;
   p.d = s.d;
@@ -340,13 +416,21 @@ int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SPFF_CUDA(cudaFuncSetAttribute(conv3_fprop_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPFF_CUDA(cudaFuncSetAttribute(conv3_fprop_kernel<KC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    L::kTotal + 1024));
     attr_set = true;
   }
   int ctas = debug_ctas() > 0 ? debug_ctas() : num_sms();
-  if (p.items < ctas) ctas = static_cast<int>(p.items);
-  conv3_fprop_kernel<KC><<<ctas, kThreads, L::kTotal + 1024, stream>>>(tx, tw, p);
+  if (RES) {
+    const long long pos_items = p.items / p.ncb;
+    long long per_cb = ctas / p.ncb;
+    if (per_cb < 1) per_cb = 1;
+    if (per_cb > pos_items) per_cb = pos_items;
+    ctas = static_cast<int>(per_cb * p.ncb);
+  } else if (p.items < ctas) {
+    ctas = static_cast<int>(p.items);
+  }
+  conv3_fprop_kernel<KC, RES><<<ctas, kThreads, L::kTotal + 1024, stream>>>(tx, tw, p);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -427,8 +511,11 @@ static int conv3_common(const void* x, long long ldx, int cin, const void* wpk, 
                    (reinterpret_cast<uintptr_t>(wpk) & 15) == 0,
                "%s: pointers must be 16-byte aligned", who);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (spff::conv3_kc(cin) == 64) return spff::launch_fprop<64>(x, ldx, cin, wpk, y, ldy, cout, s, st);
-  return spff::launch_fprop<32>(x, ldx, cin, wpk, y, ldy, cout, s, st);
+  // cin <= 64: one K chunk per tap, all 27 taps of a 32-channel output block stay resident in smem
+  if (cin == 64) return spff::launch_fprop<64, true>(x, ldx, cin, wpk, y, ldy, cout, s, st);
+  if (cin == 32) return spff::launch_fprop<32, true>(x, ldx, cin, wpk, y, ldy, cout, s, st);
+  if (spff::conv3_kc(cin) == 64) return spff::launch_fprop<64, false>(x, ldx, cin, wpk, y, ldy, cout, s, st);
+  return spff::launch_fprop<32, false>(x, ldx, cin, wpk, y, ldy, cout, s, st);
 }
 
 int spff_conv3d_k3_fwd(const void* x, long long ldx, int cin, const void* w_fwd, void* y, long long ldy, int cout,

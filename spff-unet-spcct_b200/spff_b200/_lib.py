@@ -43,9 +43,11 @@ _PROTOTYPES = {
     "spff_pack_conv3_weight": [_P, _P, _P, c_int, c_int, _P],
     "spff_conv3d_k3_fwd": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P],
     "spff_conv3d_k3_dgrad": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P],
+    "spff_conv3d_k3_wgrad_workspace": [c_int, c_int, Shape],
+    "spff_conv3d_k3_wgrad": [_P, _LL, c_int, _P, _LL, c_int, Shape, _P, c_float, _P, c_size_t, _P],
 }
 
-_SIZE_T_FUNCS = set()
+_SIZE_T_FUNCS = {"spff_conv3d_k3_wgrad_workspace"}
 
 
 def _declare():

@@ -52,3 +52,33 @@ def conv3d_k3_dgrad(dy, cout, w_dgrad, dx, cin):
     s2, lddx = _view(dx, cin)
     assert (s.n, s.d, s.h, s.w) == (s2.n, s2.d, s2.h, s2.w)
     call("spff_conv3d_k3_dgrad", ptr(dy), lddy, cout, ptr(w_dgrad), ptr(dx), lddx, cin, s, stream_ptr())
+
+
+_WS = {}
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per device (the library itself allocates nothing)."""
+    key = str(device)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def conv3d_k3_wgrad_workspace(cin, cout, x) -> torch.Tensor:
+    s, _ = _view(x, cin)
+    return workspace(int(_lib.lib.spff_conv3d_k3_wgrad_workspace(cin, cout, s)), x.device)
+
+
+def conv3d_k3_wgrad(x, cin, dy, cout, dw, beta: float = 0.0, ws: torch.Tensor | None = None):
+    """dw [Cout,Cin,3,3,3] fp32 = beta*dw + grad_weight."""
+    s, ldx = _view(x, cin)
+    s2, lddy = _view(dy, cout)
+    assert (s.n, s.d, s.h, s.w) == (s2.n, s2.d, s2.h, s2.w)
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (cout, cin, 3, 3, 3)
+    if ws is None:
+        ws = conv3d_k3_wgrad_workspace(cin, cout, x)
+    call("spff_conv3d_k3_wgrad", ptr(x), ldx, cin, ptr(dy), lddy, cout, s, ptr(dw), float(beta), ptr(ws),
+         ws.numel(), stream_ptr())

@@ -96,3 +96,40 @@ def test_conv3_fwd_strided_views():
     got = _from_ndhwc(y[..., 32:], cout)
     assert (y[..., :32] == 0).all()
     assert (got - ref).norm() / ref.norm() < 4e-3
+
+
+WG_CASES = [
+    (2, 5, 16, 16, 32, 32),
+    (1, 5, 8, 8, 64, 32),
+    (2, 5, 16, 16, 32, 64),
+    (1, 5, 16, 16, 64, 64),
+    (1, 5, 8, 8, 128, 64),
+    (1, 5, 8, 24, 32, 32),
+    (1, 3, 4, 8, 64, 128),
+    (1, 7, 8, 8, 32, 32),
+    (2, 5, 2, 2, 256, 256),
+    (3, 5, 32, 32, 32, 32),
+]
+
+
+@pytest.mark.parametrize("n,d,h,w,cin,cout", WG_CASES)
+def test_conv3_wgrad(n, d, h, w, cin, cout):
+    from spff_b200 import ops
+
+    torch.backends.cudnn.allow_tf32 = False
+    x = _mk(n, cin, d, h, w, 7)
+    dy = _mk(n, cout, d, h, w, 8)
+    xb, dyb = _to_ndhwc_bf16(x), _to_ndhwc_bf16(dy)
+    dw = torch.full((cout, cin, 3, 3, 3), float("nan"), device="cuda")
+    ops.conv3d_k3_wgrad(xb, cin, dyb, cout, dw, 0.0)
+    torch.cuda.synchronize()
+    xr = xb.float().permute(0, 4, 1, 2, 3).double()
+    dyr = dyb.float().permute(0, 4, 1, 2, 3).double()
+    ref = torch.nn.grad.conv3d_weight(xr, (cout, cin, 3, 3, 3), dyr, padding=1).float()
+    assert torch.isfinite(dw).all()
+    rel = (dw - ref).norm() / ref.norm()
+    assert rel < 1e-4, rel  # fp32 accumulation of exact bf16 products
+    # beta = 1 accumulates
+    ops.conv3d_k3_wgrad(xb, cin, dyb, cout, dw, 1.0)
+    torch.cuda.synchronize()
+    assert ((dw - 2 * ref).norm() / ref.norm()) < 2e-4
