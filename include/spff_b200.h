@@ -78,7 +78,107 @@ int spff_conv3d_k3_wgrad(const void* x, long long ldx, int cin, const void* dy, 
                          spff_shape s, float* dw, float beta, void* workspace, size_t workspace_bytes,
                          void* stream);
 
-/* @@ENTRY_POINTS@@ */
+/* ---- the Cin = 1 stem convolution (enc1.pre.0 / enc1.b1.0: `_conv3x3xk(1, 32, 3)`, models.py:616-618 with
+ * in_channels = 1 from models.py:1551) ------------------------------------------------------------
+ * x is the network input as the reference holds it: fp32 [N,1,D,H,W] contiguous. w fp32 [cout][1][3][3][3]. */
+int spff_conv3d_stem_fwd(const float* x, const float* w, void* y, long long ldy, int cout, spff_shape s,
+                         void* stream);
+size_t spff_conv3d_stem_wgrad_workspace(int cout);
+/* dw[cout][1][3][3][3] = beta*dw + gradient (per-block partials in `workspace`, fixed-order reduce). */
+int spff_conv3d_stem_wgrad(const float* x, const void* dy, long long lddy, int cout, spff_shape s, float* dw,
+                           float beta, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- ConvTranspose3d kernel = stride = (1,2,2), with bias (models.py:668-672) -------------------
+ * `s` is always the COARSE grid (input of the forward); the fine tensors are [n, d, 2h, 2w, c].
+ * Weight [cin][cout][1][2][2] fp32 -> bf16 operands  w_fwd [4][cin/KC][cout][KC],
+ * w_dgrad [4][cout/KC'][cin][KC']  (quadrant q = 2*i + j). */
+int spff_pack_convt_weight(const float* w, void* w_fwd, void* w_dgrad, int cin, int cout, void* stream);
+int spff_convt_k122_fwd(const void* x, long long ldx, int cin, const void* w_fwd, const float* bias, void* y,
+                        long long ldy, int cout, spff_shape s, void* stream);
+int spff_convt_k122_dgrad(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
+                          int cin, spff_shape s, void* stream);
+size_t spff_convt_k122_wgrad_workspace(int cin, int cout, spff_shape s);
+/* dw[cin][cout][1][2][2] = beta*dw + gradient. (The bias gradient is the column sum of dy: spff_in_stats.) */
+int spff_convt_k122_wgrad(const void* x, long long ldx, int cin, const void* dy, long long lddy, int cout,
+                          spff_shape s, float* dw, float beta, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---- InstanceNorm3d(affine, eps) + LeakyReLU + the collapsed SPFF tail ----------------------------
+ * models.py:168-181 (norm, act), :1473-1478 (block), :684-685 (_post). SURVEY.md §7.3:
+ *   a = lrelu(IN(x)),  out = a * P[n,d,c] + Q[n,d,c]. */
+/* stats[n][c]{sum, sum of squares} += over the (d,h,w) positions of x (double; caller zeroes). */
+int spff_in_stats(const void* x, long long ldx, int c, spff_shape s, double* stats, void* stream);
+/* stats over `count` elements per (n,c) -> coef[n][c] = {A, B, mean, rstd}, IN(x) = x*A + B with
+ * A = rstd*gamma[c], B = beta[c] - mean*A. batch_stats != 0: BatchNorm3d training statistics
+ * (summed over n; models.py:170-171 / Cicek3DUNet :721). */
+int spff_in_coeffs(const double* stats, const float* gamma, const float* beta, float eps, int n, int c,
+                   long long count, int batch_stats, float* coef, void* stream);
+/* y = lrelu(x*A + B) (bf16 -> bf16). */
+int spff_norm_act_apply(const void* x, long long ldx, const float* coef, void* y, long long ldy, int c, spff_shape s,
+                        float slope, void* stream);
+/* S[n][d][c] += sum_{h,w} lrelu(x*A + B)  (fp32; caller zeroes S). */
+int spff_norm_act_reduce(const void* x, long long ldx, const float* coef, float* S, int c, spff_shape s, float slope,
+                         void* stream);
+/* y = lrelu(x*A+B)*P + Q; P,Q are [n][d][c] fp32 or both NULL (identity). If ypool != NULL also
+ * writes the (1,2,2) max-pool of y (nn.MaxPool3d, models.py:658-665) to ypool [n,d,h/2,w/2] with pitch ldp. */
+int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, const float* P, const float* Q,
+                               void* y, long long ldy, void* ypool, long long ldp, int c, spff_shape s, float slope,
+                               void* stream);
+/* Gate micro-kernel: S[n][d][c] -> P,Q[n][d][c]. Tables (fp32, device): g1[c][d] = 1 + tanh(gamma),
+ * bt[c][d] = beta of EnergyFiLM (input independent, models.py:1494-1512); kfg[d]: the circular
+ * kernel irfft(freq_mask*mag_scale) of FourierGate (models.py:1537-1542); se_w1[hid][c], se_b1[hid],
+ * se_w2[c][hid], se_b2[c]: _SEChannelLite fc (models.py:604-607). Unused ones NULL. */
+int spff_gate_micro_fwd(const float* S, const float* g1, const float* bt, const float* kfg, const float* se_w1,
+                        const float* se_b1, const float* se_w2, const float* se_b2, int hid, int flags, int c,
+                        spff_shape s, float* P, float* Q, void* stream);
+/* Backward pass 1: R[n][d][c][6] += per-plane sums over (h,w) of
+ *   {dout*a, dout, dout*m, m, dout*m*xhat, m*xhat},  m = lrelu'(z), z = x*A+B, a = lrelu(z). */
+int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
+                             float* R, int c, spff_shape s, float slope, void* stream);
+/* Backward micro-kernel: consumes R (and S), recomputes the gates, produces
+ *   bcoef[n][c] = {gamma*rstd, mean(dz), mean(dz*xhat), 0}, dSa[n][d][c], Pout[n][d][c]
+ * and ACCUMULATES (+=) dgamma[c], dbeta[c], dg1[c][d], dbt[c][d], dkfg[d], dse_*. flags == 0 is the
+ * plain InstanceNorm+LeakyReLU backward (S, dSa, Pout and the gate tables may be NULL). */
+int spff_gate_micro_bwd(const float* R, const float* S, const float* coef, const float* gamma, const float* g1,
+                        const float* bt, const float* kfg, const float* se_w1, const float* se_b1,
+                        const float* se_w2, const float* se_b2, int hid, int flags, int c, spff_shape s,
+                        float* bcoef, float* dSa, float* Pout, float* dgamma, float* dbeta, float* dg1, float* dbt,
+                        float* dkfg, float* dse_w1, float* dse_b1, float* dse_w2, float* dse_b2, void* stream);
+/* Backward pass 2: dx = c1*(dz - c2 - xhat*c3), dz = (dout*P + dSa)*m. P/dSa both NULL: P = 1, dSa = 0. */
+int spff_norm_act_bwd_apply(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
+                            const float* bcoef, const float* P, const float* dSa, void* dx, long long lddx, int c,
+                            spff_shape s, float slope, void* stream);
+/* Max-pool (1,2,2) backward fused with the skip add: dskip (full res) = (accumulate ? dskip : 0) +
+ * scatter(dpool) at the arg-max of y in each 2x2 window (first max wins, as ATen). `s` = full-res grid. */
+int spff_maxpool_bwd_add(const void* dpool, long long ldp, const void* y, long long ldy, void* dskip, long long ldd,
+                         int c, spff_shape s, int accumulate, void* stream);
+
+/* ---- head (1x1x1 conv + bias, models.py:674) and loss (helpers.py:782-803) ------------------------ */
+/* logits fp32 [N,K,D,H,W] = x[pos][0..32) . w[K][32] + b[K]   (cin must be 32, K <= 16). */
+int spff_head_fwd(const void* x, long long ldx, int cin, const float* w, const float* b, float* logits, int k,
+                  spff_shape s, void* stream);
+/* labels uint8 [N,D,H,W] = argmax_k (first max wins, torch.argmax) — inference path. */
+int spff_head_argmax(const void* x, long long ldx, int cin, const float* w, const float* b, uint8_t* labels, int k,
+                     spff_shape s, void* stream);
+size_t spff_head_bwd_workspace(int k);
+/* dx (bf16, may be NULL) = dlogits . w ; dw[K][32], db[K] = beta*old + gradient. */
+int spff_head_bwd(const float* dlogits, const void* x, long long ldx, int cin, const float* w, void* dx,
+                  long long lddx, float* dw, float* db, float beta, int k, spff_shape s, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* Cross-entropy + hard confusion tally over logits fp32 [N,K,D,H,W] (F.cross_entropy(ignore_index)
+ * helpers.py:798-801; the counts of helpers.py:687-690, 716-719, 789-791):
+ *   acc[0] += sum of nll over valid voxels (double), counts[0] += #valid (int64),
+ *   confusion[K][K] (int64, [label][argmax]) += tallies.  label_bytes = 1 (uint8) or 8 (int64). */
+int spff_ce_confusion(const float* logits, const void* labels, int label_bytes, int ignore_index, int k,
+                      spff_shape s, double* acc, long long* counts, long long* confusion, void* stream);
+/* dlogits = (softmax - onehot) * gscale[0] / n_valid[0] on valid voxels, 0 on ignored ones
+ * (gscale may be NULL = 1). */
+int spff_ce_grad(const float* logits, const void* labels, int label_bytes, int ignore_index, int k, spff_shape s,
+                 const long long* n_valid, const float* gscale, float* dlogits, void* stream);
+
+/* ---- optimizer (models.py:591-594: torch.optim.Adam, lr 1e-4, betas (0.9,0.999), eps 1e-8) -------- */
+int spff_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,590 @@
+// Bandwidth-bound kernels around the convolutions: InstanceNorm3d statistics and apply, LeakyReLU,
+// the collapsed SPFF tail  out = lrelu(IN(x)) * P[n,d,c] + Q[n,d,c]  (SURVEY.md §7.3), the fused
+// (1,2,2) max-pool, and the matching backward passes. They replace nn.InstanceNorm3d / LeakyReLU
+// (reference innovative3D/models.py:168-181), the elementwise halves of EnergyFiLM3D / FourierGate3D /
+// _SpectralSE / _SEChannelLite (models.py:1505-1512, 1527-1544, 600-614) and nn.MaxPool3d((1,2,2))
+// (models.py:658-665).
+//
+// Access pattern: activations are position-major bf16 [positions][ld]; a thread owns one 16-byte
+// vector (8 channels) of a position, so a warp reads/writes 512 contiguous bytes per instruction and
+// its per-channel coefficients (A, B, P, Q ...) stay in registers for a whole (sample, plane) chunk.
+// Reductions over positions are per-thread fp32 partials -> shared-memory tree across the threads
+// that own the same channels -> one atomic per channel per block.
+#include "common.h"
+
+#include <cuda_bf16.h>
+
+namespace spff {
+namespace {
+
+constexpr int kBlock = 256;
+
+struct PlaneGrid {
+  int c8;     // 16-byte vectors per position (C / 8)
+  int rpi;    // positions ("rows") per block iteration = kBlock / c8
+  int hw;     // positions per plane
+  int chunk;  // positions per block
+};
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// Sum `NV` per-thread values over the threads of the block that own the same channel vector
+// (same tid % c8); the result is valid in the threads with tid < c8. `red` holds NV*kBlock floats.
+template <int NV>
+__device__ __forceinline__ void reduce_rows(float (&v)[NV], float* red, int c8, int rpi) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) red[i * kBlock + tid] = v[i];
+  __syncthreads();
+  if (tid < c8) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float s = 0.f;
+      for (int r = 0; r < rpi; ++r) s += red[i * kBlock + r * c8 + tid];
+      v[i] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm statistics: stats[n][c] += {sum x, sum x^2} over the block's positions (double).
+// grid = (chunks, d, n)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) in_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+                                                          PlaneGrid g, int d, double* __restrict__ stats, int c) {
+  extern __shared__ float red[];
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
+  const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (r < g.rpi) {
+    for (int p = p0 + r; p < p1; p += g.rpi) {
+      float f[8];
+      unpack8(ldg16(x + (base + p) * ld + v * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] = fmaf(f[i], f[i], q[i]);
+      }
+    }
+  }
+  float sq[16];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sq[i] = s[i];
+    sq[8 + i] = q[i];
+  }
+  reduce_rows<16>(sq, red, g.c8, g.rpi);
+  if (threadIdx.x < g.c8) {
+    double* dst = stats + (static_cast<long long>(n) * c + v * 8) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(dst + 2 * i, static_cast<double>(sq[i]));
+      atomicAdd(dst + 2 * i + 1, static_cast<double>(sq[8 + i]));
+    }
+  }
+}
+
+// coef[n][c] = {A, B, mean, rstd}: IN(x) = x*A + B with A = rstd*gamma, B = beta - mean*A.
+// batch_stats != 0 (BatchNorm3d training mode): statistics are summed over the samples first.
+__global__ void in_coeffs_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, int n, int c, double count,
+                                 int batch_stats, float* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int ch = i % c;
+  double s = 0, q = 0, cnt = count;
+  if (batch_stats) {
+    for (int k = 0; k < n; ++k) {
+      s += stats[(static_cast<long long>(k) * c + ch) * 2];
+      q += stats[(static_cast<long long>(k) * c + ch) * 2 + 1];
+    }
+    cnt = count * n;
+  } else {
+    s = stats[static_cast<long long>(i) * 2];
+    q = stats[static_cast<long long>(i) * 2 + 1];
+  }
+  const double mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float ga = gamma ? gamma[ch] : 1.f;
+  const float be = beta ? beta[ch] : 0.f;
+  const float A = rstd * ga;
+  float4 o;
+  o.x = A;
+  o.y = be - static_cast<float>(mean) * A;
+  o.z = static_cast<float>(mean);
+  o.w = rstd;
+  reinterpret_cast<float4*>(coef)[i] = o;
+}
+
+__device__ __forceinline__ void load_ab(const float* __restrict__ coef, int n, int c, int v, float (&A)[8],
+                                        float (&B)[8]) {
+  const float4* cf = reinterpret_cast<const float4*>(coef) + static_cast<long long>(n) * c + v * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = __ldg(cf + i);
+    A[i] = t.x;
+    B[i] = t.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+  o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// y = lrelu(x*A+B) [* P + Q]   and/or   S[n][d][c] += sum_hw lrelu(x*A+B).   grid = (chunks, d, n)
+// ---------------------------------------------------------------------------------------------
+template <bool WRITE, bool REDUCE, bool AFFINE>
+__global__ void __launch_bounds__(kBlock)
+norm_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ coef,
+                const float* __restrict__ P, const float* __restrict__ Q, __nv_bfloat16* __restrict__ y,
+                long long ldy, float* __restrict__ S, PlaneGrid g, int d, int c, float slope) {
+  extern __shared__ float red[];
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
+  const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  float A[8], B[8], Pv[8], Qv[8], acc[8];
+  load_ab(coef, n, c, v, A, B);
+  if (AFFINE) {
+    const long long pq = (static_cast<long long>(n) * d + dd) * c + v * 8;
+    load8(P + pq, Pv);
+    load8(Q + pq, Qv);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (r < g.rpi) {
+    for (int p = p0 + r; p < p1; p += g.rpi) {
+      float f[8];
+      unpack8(ldg16(x + (base + p) * ldx + v * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float z = fmaf(f[i], A[i], B[i]);
+        float a = z > 0.f ? z : z * slope;
+        if (REDUCE) acc[i] += a;
+        f[i] = AFFINE ? fmaf(a, Pv[i], Qv[i]) : a;
+      }
+      if (WRITE) stg16(y + (base + p) * ldy + v * 8, pack8(f));
+    }
+  }
+  if (REDUCE) {
+    reduce_rows<8>(acc, red, g.c8, g.rpi);
+    if (threadIdx.x < g.c8) {
+      float* dst = S + (static_cast<long long>(n) * d + dd) * c + v * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(dst + i, acc[i]);
+    }
+  }
+}
+
+// out = lrelu(x*A+B)*P+Q written at full resolution AND its (1,2,2) max-pool. A thread owns the
+// 2x2 window of one pooled position. grid = (chunks over pooled positions, d, n). h, w even.
+template <bool AFFINE>
+__global__ void __launch_bounds__(kBlock)
+norm_act_pool_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ coef,
+                     const float* __restrict__ P, const float* __restrict__ Q, __nv_bfloat16* __restrict__ y,
+                     long long ldy, __nv_bfloat16* __restrict__ yp, long long ldp, PlaneGrid g, int d, int c, int h,
+                     int w, float slope) {
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
+  const int w2 = w / 2;
+  const long long base = (static_cast<long long>(n) * d + dd) * (static_cast<long long>(h) * w);
+  const long long basep = (static_cast<long long>(n) * d + dd) * g.hw;  // g.hw = pooled positions per plane
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  float A[8], B[8], Pv[8], Qv[8];
+  load_ab(coef, n, c, v, A, B);
+  if (AFFINE) {
+    const long long pq = (static_cast<long long>(n) * d + dd) * c + v * 8;
+    load8(P + pq, Pv);
+    load8(Q + pq, Qv);
+  }
+  if (r >= g.rpi) return;
+  for (int p = p0 + r; p < p1; p += g.rpi) {
+    const int hp = p / w2, wp = p % w2;
+    float mx[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long pos = base + static_cast<long long>(2 * hp + (k >> 1)) * w + 2 * wp + (k & 1);
+      float f[8];
+      unpack8(ldg16(x + pos * ldx + v * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float z = fmaf(f[i], A[i], B[i]);
+        float a = z > 0.f ? z : z * slope;
+        f[i] = AFFINE ? fmaf(a, Pv[i], Qv[i]) : a;
+      }
+      const uint4 o = pack8(f);
+      stg16(y + pos * ldy + v * 8, o);
+      unpack8(o, f);  // pool the values as stored (bf16), so that backward finds the same arg-max
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = (k == 0) ? f[i] : fmaxf(mx[i], f[i]);
+    }
+    stg16(yp + (basep + p) * ldp + v * 8, pack8(mx));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward pass 1: R[n][d][c][6] += sums over (h,w) of
+//   {dout*a, dout, dout*m, m, dout*m*xhat, m*xhat},  z = x*A+B, m = lrelu'(z), a = lrelu(z),
+//   xhat = (x-mean)*rstd.     grid = (chunks, d, n)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ x,
+                           long long ldx, const float* __restrict__ coef, float* __restrict__ R, PlaneGrid g, int d,
+                           int c, float slope) {
+  extern __shared__ float red[];
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
+  const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  float A[8], B[8], Mn[8], Rs[8];
+  {
+    const float4* cf = reinterpret_cast<const float4*>(coef) + static_cast<long long>(n) * c + v * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = __ldg(cf + i);
+      A[i] = t.x; B[i] = t.y; Mn[i] = t.z; Rs[i] = t.w;
+    }
+  }
+  float acc[6][8];
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+  if (r < g.rpi) {
+    for (int p = p0 + r; p < p1; p += g.rpi) {
+      float f[8], go[8];
+      unpack8(ldg16(x + (base + p) * ldx + v * 8), f);
+      unpack8(ldg16(dout + (base + p) * lddo + v * 8), go);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float z = fmaf(f[i], A[i], B[i]);
+        const float m = z > 0.f ? 1.f : slope;
+        const float a = z * m;
+        const float xh = (f[i] - Mn[i]) * Rs[i];
+        const float gm = go[i] * m;
+        acc[0][i] = fmaf(go[i], a, acc[0][i]);
+        acc[1][i] += go[i];
+        acc[2][i] += gm;
+        acc[3][i] += m;
+        acc[4][i] = fmaf(gm, xh, acc[4][i]);
+        acc[5][i] = fmaf(m, xh, acc[5][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    reduce_rows<8>(acc[k], red, g.c8, g.rpi);
+    if (threadIdx.x < g.c8) {
+      float* dst = R + ((static_cast<long long>(n) * d + dd) * c + v * 8) * 6 + k;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(dst + 6 * i, acc[k][i]);
+    }
+  }
+}
+
+// backward pass 2: dx = c1*(dz - c2 - xhat*c3), dz = (dout*P + dSa)*m.  bcoef[n][c] = {c1,c2,c3,-}
+template <bool AFFINE>
+__global__ void __launch_bounds__(kBlock)
+norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ x,
+                          long long ldx, const float* __restrict__ coef, const float* __restrict__ bcoef,
+                          const float* __restrict__ P, const float* __restrict__ dSa, __nv_bfloat16* __restrict__ dx,
+                          long long lddx, PlaneGrid g, int d, int c, float slope) {
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
+  const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  float A[8], B[8], Mn[8], Rs[8], C1[8], C2[8], C3[8], Pv[8], Dv[8];
+  {
+    const float4* cf = reinterpret_cast<const float4*>(coef) + static_cast<long long>(n) * c + v * 8;
+    const float4* bf = reinterpret_cast<const float4*>(bcoef) + static_cast<long long>(n) * c + v * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = __ldg(cf + i);
+      A[i] = t.x; B[i] = t.y; Mn[i] = t.z; Rs[i] = t.w;
+      float4 u = __ldg(bf + i);
+      C1[i] = u.x; C2[i] = u.y; C3[i] = u.z;
+    }
+  }
+  if (AFFINE) {
+    const long long pq = (static_cast<long long>(n) * d + dd) * c + v * 8;
+    load8(P + pq, Pv);
+    load8(dSa + pq, Dv);
+  }
+  if (r >= g.rpi) return;
+  for (int p = p0 + r; p < p1; p += g.rpi) {
+    float f[8], go[8];
+    unpack8(ldg16(x + (base + p) * ldx + v * 8), f);
+    unpack8(ldg16(dout + (base + p) * lddo + v * 8), go);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float z = fmaf(f[i], A[i], B[i]);
+      const float m = z > 0.f ? 1.f : slope;
+      const float xh = (f[i] - Mn[i]) * Rs[i];
+      const float da = AFFINE ? fmaf(go[i], Pv[i], Dv[i]) : go[i];
+      const float dz = da * m;
+      f[i] = C1[i] * (dz - C2[i] - xh * C3[i]);
+    }
+    stg16(dx + (base + p) * lddx + v * 8, pack8(f));
+  }
+}
+
+// (1,2,2) max-pool backward fused with the skip add: dskip[arg-max of y in the window] += dpool.
+// grid = (chunks over pooled positions, d, n)
+__global__ void __launch_bounds__(kBlock)
+maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ dpool, long long ldp, const __nv_bfloat16* __restrict__ y,
+                       long long ldy, __nv_bfloat16* __restrict__ dskip, long long ldd, PlaneGrid g, int d, int h, int w,
+                       int accumulate) {
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
+  const int w2 = w / 2;
+  const long long base = (static_cast<long long>(n) * d + dd) * (static_cast<long long>(h) * w);
+  const long long basep = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  if (r >= g.rpi) return;
+  for (int p = p0 + r; p < p1; p += g.rpi) {
+    const int hp = p / w2, wp = p % w2;
+    float gp[8], yv[4][8];
+    unpack8(ldg16(dpool + (basep + p) * ldp + v * 8), gp);
+    long long pos[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pos[k] = base + static_cast<long long>(2 * hp + (k >> 1)) * w + 2 * wp + (k & 1);
+      unpack8(ldg16(y + pos[k] * ldy + v * 8), yv[k]);
+    }
+    int arg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int a = 0;
+      float best = yv[0][i];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (yv[k][i] > best) {
+          best = yv[k][i];
+          a = k;
+        }
+      arg[i] = a;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+      if (accumulate) {
+        unpack8(*reinterpret_cast<const uint4*>(dskip + pos[k] * ldd + v * 8), o);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += (arg[i] == k) ? gp[i] : 0.f;
+      stg16(dskip + pos[k] * ldd + v * 8, pack8(o));
+    }
+  }
+}
+
+int make_grid(int c, long long hw, spff_shape s, PlaneGrid* g, dim3* grid) {
+  if (c % 8 != 0 || c <= 0 || c > 8 * kBlock) {
+    set_error("channel count %d must be a multiple of 8 and <= %d", c, 8 * kBlock);
+    return SPFF_ERR_BAD_ARGUMENT;
+  }
+  g->c8 = c / 8;
+  g->rpi = kBlock / g->c8;
+  g->hw = static_cast<int>(hw);
+  // aim at >= ~8 blocks per SM overall while keeping >= 16 iterations per block where the plane allows
+  const long long planes = static_cast<long long>(s.n) * s.d;
+  long long want_chunks = (8LL * num_sms() + planes - 1) / planes;
+  if (want_chunks < 1) want_chunks = 1;
+  long long chunk = (hw + want_chunks - 1) / want_chunks;
+  const long long min_chunk = 16LL * g->rpi;
+  if (chunk < min_chunk) chunk = min_chunk;
+  chunk = ((chunk + g->rpi - 1) / g->rpi) * g->rpi;
+  g->chunk = static_cast<int>(chunk);
+  const int chunks = static_cast<int>((hw + chunk - 1) / chunk);
+  *grid = dim3(chunks, s.d, s.n);
+  if (s.d > 65535 || s.n > 65535) {
+    set_error("too many planes/samples for one launch");
+    return SPFF_ERR_BAD_ARGUMENT;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace spff
+
+using spff::kBlock;
+using spff::PlaneGrid;
+typedef __nv_bfloat16 bf16;
+
+#define SPFF_ENTRY_CHECK()          \
+  do {                              \
+    int _e = spff_device_check();   \
+    if (_e) return _e;              \
+  } while (0)
+
+extern "C" {
+
+int spff_in_stats(const void* x, long long ldx, int c, spff_shape s, double* stats, void* stream) {
+  SPFF_ENTRY_CHECK();
+  PlaneGrid g;
+  dim3 grid;
+  int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
+  if (e) return e;
+  spff::in_stats_kernel<<<grid, kBlock, 16 * kBlock * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x), ldx, g, s.d, stats, c);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_in_coeffs(const double* stats, const float* gamma, const float* beta, float eps, int n, int c,
+                   long long count, int batch_stats, float* coef, void* stream) {
+  SPFF_ENTRY_CHECK();
+  const int total = n * c;
+  spff::in_coeffs_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, gamma, beta, eps, n, c, static_cast<double>(count), batch_stats, coef);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_norm_act_apply(const void* x, long long ldx, const float* coef, void* y, long long ldy, int c, spff_shape s,
+                        float slope, void* stream) {
+  SPFF_ENTRY_CHECK();
+  PlaneGrid g;
+  dim3 grid;
+  int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
+  if (e) return e;
+  spff::norm_act_kernel<true, false, false><<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x), ldx, coef, nullptr, nullptr, static_cast<bf16*>(y), ldy, nullptr, g, s.d, c, slope);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_norm_act_reduce(const void* x, long long ldx, const float* coef, float* S, int c, spff_shape s, float slope,
+                         void* stream) {
+  SPFF_ENTRY_CHECK();
+  PlaneGrid g;
+  dim3 grid;
+  int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
+  if (e) return e;
+  spff::norm_act_kernel<false, true, false>
+      <<<grid, kBlock, 8 * kBlock * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+          static_cast<const bf16*>(x), ldx, coef, nullptr, nullptr, nullptr, 0, S, g, s.d, c, slope);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, const float* P, const float* Q,
+                               void* y, long long ldy, void* ypool, long long ldp, int c, spff_shape s, float slope,
+                               void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE((P == nullptr) == (Q == nullptr), "norm_act_affine_apply: P and Q must both be given or both be NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PlaneGrid g;
+  dim3 grid;
+  if (ypool) {
+    SPFF_REQUIRE(s.h % 2 == 0 && s.w % 2 == 0, "norm_act_affine_apply: pooling needs even H, W (got %d x %d)", s.h, s.w);
+    int e = spff::make_grid(c, static_cast<long long>(s.h / 2) * (s.w / 2), s, &g, &grid);
+    if (e) return e;
+    if (P)
+      spff::norm_act_pool_kernel<true><<<grid, kBlock, 0, st>>>(static_cast<const bf16*>(x), ldx, coef, P, Q,
+                                                               static_cast<bf16*>(y), ldy, static_cast<bf16*>(ypool),
+                                                               ldp, g, s.d, c, s.h, s.w, slope);
+    else
+      spff::norm_act_pool_kernel<false><<<grid, kBlock, 0, st>>>(static_cast<const bf16*>(x), ldx, coef, P, Q,
+                                                                static_cast<bf16*>(y), ldy, static_cast<bf16*>(ypool),
+                                                                ldp, g, s.d, c, s.h, s.w, slope);
+  } else {
+    int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
+    if (e) return e;
+    if (P)
+      spff::norm_act_kernel<true, false, true><<<grid, kBlock, 0, st>>>(
+          static_cast<const bf16*>(x), ldx, coef, P, Q, static_cast<bf16*>(y), ldy, nullptr, g, s.d, c, slope);
+    else
+      spff::norm_act_kernel<true, false, false><<<grid, kBlock, 0, st>>>(
+          static_cast<const bf16*>(x), ldx, coef, P, Q, static_cast<bf16*>(y), ldy, nullptr, g, s.d, c, slope);
+  }
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
+                             float* R, int c, spff_shape s, float slope, void* stream) {
+  SPFF_ENTRY_CHECK();
+  PlaneGrid g;
+  dim3 grid;
+  int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
+  if (e) return e;
+  spff::norm_act_bwd_reduce_kernel<<<grid, kBlock, 8 * kBlock * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g, s.d, c, slope);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_norm_act_bwd_apply(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
+                            const float* bcoef, const float* P, const float* dSa, void* dx, long long lddx, int c,
+                            spff_shape s, float slope, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE((P == nullptr) == (dSa == nullptr), "norm_act_bwd_apply: P and dSa must both be given or both be NULL");
+  PlaneGrid g;
+  dim3 grid;
+  int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
+  if (e) return e;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (P)
+    spff::norm_act_bwd_apply_kernel<true><<<grid, kBlock, 0, st>>>(static_cast<const bf16*>(dout), lddo,
+                                                                  static_cast<const bf16*>(x), ldx, coef, bcoef, P, dSa,
+                                                                  static_cast<bf16*>(dx), lddx, g, s.d, c, slope);
+  else
+    spff::norm_act_bwd_apply_kernel<false><<<grid, kBlock, 0, st>>>(static_cast<const bf16*>(dout), lddo,
+                                                                   static_cast<const bf16*>(x), ldx, coef, bcoef, P, dSa,
+                                                                   static_cast<bf16*>(dx), lddx, g, s.d, c, slope);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_maxpool_bwd_add(const void* dpool, long long ldp, const void* y, long long ldy, void* dskip, long long ldd,
+                         int c, spff_shape s, int accumulate, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(s.h % 2 == 0 && s.w % 2 == 0, "maxpool_bwd_add: needs even H, W");
+  PlaneGrid g;
+  dim3 grid;
+  int e = spff::make_grid(c, static_cast<long long>(s.h / 2) * (s.w / 2), s, &g, &grid);
+  if (e) return e;
+  spff::maxpool_bwd_add_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(dpool), ldp, static_cast<const bf16*>(y), ldy, static_cast<bf16*>(dskip), ldd, g, s.d,
+      s.h, s.w, accumulate);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,571 @@
+// CUDA-core kernels of the hot path that are not GEMM-shaped enough for the tensor pipe:
+//   * the Cin = 1 stem convolution (enc1.pre.0 / enc1.b1.0, reference innovative3D/models.py:616-618
+//     with in_channels = 1, models.py:1551) — 27 taps x 32 outputs per voxel, forward and weight
+//     gradient (the network input needs no gradient);
+//   * the 1x1x1 classification head nn.Conv3d(32, num_classes, 1) (models.py:674) forward, arg-max
+//     and backward;
+//   * cross-entropy with ignore_index + the hard confusion tally that macro_dice_loss and
+//     per_class_metrics_3d derive all their counts from (innovative3D/helpers.py:668-725, 782-803);
+//   * Adam (BaseLitModel.configure_optimizers, models.py:591-594).
+// All are bandwidth-bound: one thread per voxel (or per 16-byte channel vector), coalesced
+// accesses, weights broadcast from constant / shared memory.
+#include "common.h"
+
+#include <cuda_bf16.h>
+
+namespace spff {
+namespace {
+
+constexpr int kMaxK = 16;     // classes
+constexpr int kHeadC = 32;    // head input channels
+constexpr int kStemCo = 32;   // stem output channels
+
+__constant__ float c_head_w[kMaxK * kHeadC];
+__constant__ float c_head_b[kMaxK];
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem: y[pos][co] = sum_tap x[pos+tap] * w[co][tap]     x fp32 [N,1,D,H,W], y bf16 position-major
+// one thread = one voxel x 8 output channels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
+                int cout, spff_shape s) {
+  extern __shared__ float sw[];  // [27][cout]
+  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) sw[(i % 27) * cout + i / 27] = w[i];
+  __syncthreads();
+  const int c8 = cout / 8;
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % c8);
+    const long long pos = i / c8;
+    const int wq = static_cast<int>(pos % s.w);
+    const int hq = static_cast<int>((pos / s.w) % s.h);
+    const int dq = static_cast<int>((pos / (static_cast<long long>(s.w) * s.h)) % s.d);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const int d2 = dq + kd - 1;
+      if (d2 < 0 || d2 >= s.d) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h2 = hq + kh - 1;
+        if (h2 < 0 || h2 >= s.h) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int w2 = wq + kw - 1;
+          if (w2 < 0 || w2 >= s.w) continue;
+          const float xv = __ldg(x + pos + (static_cast<long long>(kd - 1) * s.h + (kh - 1)) * s.w + (kw - 1));
+          const float* wr = sw + ((kd * 3 + kh) * 3 + kw) * cout + v * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wr[k], acc[k]);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(y + pos * ldy + v * 8) = pack8(acc);
+  }
+}
+
+// stem weight gradient: partial[block][tap][co] = sum over the block's voxels of dy[pos][co]*x[pos+tap]
+// one thread = one voxel x 4 channels; all 27 taps accumulate in registers.
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long lddy, int cout,
+                  spff_shape s, float* __restrict__ partial) {
+  extern __shared__ float red[];  // [warps][27][cout]
+  const int c4 = cout / 4;        // channel quads per voxel (must divide 32)
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w * c4;
+  float acc[27][4];
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[t][k] = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % c4);
+    const long long pos = i / c4;
+    const int wq = static_cast<int>(pos % s.w);
+    const int hq = static_cast<int>((pos / s.w) % s.h);
+    const int dq = static_cast<int>((pos / (static_cast<long long>(s.w) * s.h)) % s.d);
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(dy + pos * lddy + v * 4));
+    const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const int d2 = dq + kd - 1;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h2 = hq + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int w2 = wq + kw - 1;
+          const bool ok = d2 >= 0 && d2 < s.d && h2 >= 0 && h2 < s.h && w2 >= 0 && w2 < s.w;
+          const float xv =
+              ok ? __ldg(x + pos + (static_cast<long long>(kd - 1) * s.h + (kh - 1)) * s.w + (kw - 1)) : 0.f;
+          const int t = (kd * 3 + kh) * 3 + kw;
+          acc[t][0] = fmaf(g01.x, xv, acc[t][0]);
+          acc[t][1] = fmaf(g01.y, xv, acc[t][1]);
+          acc[t][2] = fmaf(g23.x, xv, acc[t][2]);
+          acc[t][3] = fmaf(g23.y, xv, acc[t][3]);
+        }
+      }
+    }
+  }
+  // lanes with the same (lane % c4) own the same channels (blockDim and gridDim*blockDim are multiples of c4)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int t = 0; t < 27; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = acc[t][k];
+      for (int o = 16; o >= c4; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < c4) red[(warp * 27 + t) * cout + lane * 4 + k] = v;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
+    float v = 0.f;
+    for (int wv = 0; wv < nwarps; ++wv) v += red[wv * 27 * cout + i];
+    partial[static_cast<size_t>(blockIdx.x) * 27 * cout + i] = v;
+  }
+}
+
+// dw[co][tap] = beta*dw + sum_blocks partial[block][tap][co]
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, int blocks, int cout, float beta,
+                                         float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // index into [tap][co]
+  if (i >= 27 * cout) return;
+  float v = 0.f;
+  for (int b = 0; b < blocks; ++b) v += partial[static_cast<size_t>(b) * 27 * cout + i];
+  const int t = i / cout, co = i % cout;
+  float* dst = dw + co * 27 + t;
+  *dst = (beta == 0.f) ? v : fmaf(beta, *dst, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// head: logits[n][k][d][hw] = b[k] + sum_c x[pos][c] * w[k][c]   (weights in constant memory)
+// ---------------------------------------------------------------------------------------------
+template <bool ARGMAX>
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, float* __restrict__ logits,
+                uint8_t* __restrict__ labels, int K, long long dhw, long long total) {
+  for (long long pos = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pos < total;
+       pos += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float xv[kHeadC];
+#pragma unroll
+    for (int v = 0; v < kHeadC / 8; ++v) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + pos * ldx) + v), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[v * 8 + i] = f[i];
+    }
+    const long long n = pos / dhw, r = pos % dhw;
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+      if (k < K) {
+        float a = c_head_b[k];
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) a = fmaf(xv[c], c_head_w[k * kHeadC + c], a);
+        if (ARGMAX) {
+          if (a > best) {
+            best = a;
+            arg = k;
+          }
+        } else {
+          logits[(n * K + k) * dhw + r] = a;
+        }
+      }
+    }
+    if (ARGMAX) labels[pos] = static_cast<uint8_t>(arg);
+  }
+}
+
+// head backward: one thread = one voxel x 8 channels.
+//   dx[pos][c] = sum_k dl[k][pos] * w[k][c];  partial dW[k][c], db[k] per block -> workspace
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ dlogits, const __nv_bfloat16* __restrict__ x, long long ldx,
+                __nv_bfloat16* __restrict__ dx, long long lddx, int K, long long dhw, long long total,
+                float* __restrict__ partial /* [block][K*32 + K] */) {
+  extern __shared__ float red[];  // [warps][kMaxK*8*4 + kMaxK]
+  constexpr int V = kHeadC / 8;   // 4 threads per voxel
+  float accw[kMaxK][8];
+  float accb[kMaxK];
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) {
+    accb[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) accw[k][i] = 0.f;
+  }
+  const int v = threadIdx.x % V;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total * V;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pos = i / V;
+    const long long n = pos / dhw, r = pos % dhw;
+    float f[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + pos * ldx) + v), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+      if (k < K) {
+        const float g = __ldg(dlogits + (n * K + k) * dhw + r);
+        accb[k] += g;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          accw[k][c] = fmaf(g, f[c], accw[k][c]);
+          o[c] = fmaf(g, c_head_w[k * kHeadC + v * 8 + c], o[c]);
+        }
+      }
+    }
+    if (dx) *reinterpret_cast<uint4*>(dx + pos * lddx + v * 8) = pack8(o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int stride = kMaxK * kHeadC + kMaxK;
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) {
+    if (k < K) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float t = accw[k][c];
+        for (int off = 16; off >= V; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane < V) red[warp * stride + k * kHeadC + lane * 8 + c] = t;
+      }
+      float t = (v == 0) ? accb[k] : 0.f;
+      for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      if (lane == 0) red[warp * stride + kMaxK * kHeadC + k] = t;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * kHeadC + K; i += blockDim.x) {
+    const int src = i < K * kHeadC ? i : kMaxK * kHeadC + (i - K * kHeadC);
+    float t = 0.f;
+    for (int wv = 0; wv < nwarps; ++wv) t += red[wv * stride + src];
+    partial[static_cast<size_t>(blockIdx.x) * (K * kHeadC + K) + i] = t;
+  }
+}
+
+__global__ void head_bwd_reduce_kernel(const float* __restrict__ partial, int blocks, int K, float beta,
+                                       float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tot = K * kHeadC + K;
+  if (i >= tot) return;
+  float t = 0.f;
+  for (int b = 0; b < blocks; ++b) t += partial[static_cast<size_t>(b) * tot + i];
+  float* dst = i < K * kHeadC ? dw + i : db + (i - K * kHeadC);
+  *dst = (beta == 0.f) ? t : fmaf(beta, *dst, t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cross entropy + confusion tally over fp32 logits [N,K,D,H,W]
+// ---------------------------------------------------------------------------------------------
+template <typename LabelT>
+__device__ __forceinline__ int load_label(const void* labels, long long i) {
+  return static_cast<int>(static_cast<const LabelT*>(labels)[i]);
+}
+
+template <typename LabelT, bool GRAD>
+__global__ void __launch_bounds__(256)
+ce_kernel(const float* __restrict__ logits, const void* __restrict__ labels, int ignore_index, int K, long long dhw,
+          long long total, double* __restrict__ acc, unsigned long long* __restrict__ counts,
+          unsigned long long* __restrict__ confusion, const unsigned long long* __restrict__ n_valid,
+          const float* __restrict__ gscale, float* __restrict__ dlogits) {
+  __shared__ unsigned int s_conf[kMaxK * kMaxK];
+  __shared__ float s_nll[8];
+  __shared__ unsigned int s_cnt[8];
+  if (!GRAD) {
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) s_conf[i] = 0;
+    __syncthreads();
+  }
+  float scale = 0.f;
+  if (GRAD) {
+    const unsigned long long nv = n_valid[0];
+    scale = (nv > 0 ? 1.f / static_cast<float>(nv) : 0.f) * (gscale ? gscale[0] : 1.f);
+  }
+  float nll_sum = 0.f;
+  unsigned int cnt = 0;
+  for (long long pos = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pos < total;
+       pos += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = pos / dhw, r = pos % dhw;
+    const int lab = load_label<LabelT>(labels, pos);
+    const bool valid = lab != ignore_index;
+    float l[kMaxK];
+    float mx = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+      if (k < K) {
+        l[k] = __ldg(logits + (n * K + k) * dhw + r);
+        if (l[k] > mx) {
+          mx = l[k];
+          arg = k;
+        }
+      }
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k)
+      if (k < K) se += __expf(l[k] - mx);
+    if (GRAD) {
+      const float inv = 1.f / se;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        if (k < K) {
+          float g = 0.f;
+          if (valid) g = (__expf(l[k] - mx) * inv - (k == lab ? 1.f : 0.f)) * scale;
+          dlogits[(n * K + k) * dhw + r] = g;
+        }
+    } else if (valid) {
+      float ll = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        if (k < K && k == lab) ll = l[k];
+      nll_sum += (mx + __logf(se)) - ll;
+      ++cnt;
+      if (lab >= 0 && lab < K) atomicAdd(&s_conf[lab * K + arg], 1u);
+    }
+  }
+  if (!GRAD) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) {
+      nll_sum += __shfl_xor_sync(0xffffffffu, nll_sum, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
+      s_nll[warp] = nll_sum;
+      s_cnt[warp] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      unsigned long long c = 0;
+      for (int wv = 0; wv < (blockDim.x >> 5); ++wv) {
+        t += s_nll[wv];
+        c += s_cnt[wv];
+      }
+      atomicAdd(acc, t);
+      atomicAdd(counts, c);
+    }
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+      if (s_conf[i]) atomicAdd(confusion + i, static_cast<unsigned long long>(s_conf[i]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics, no weight decay / amsgrad)
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+int grid_for(long long work_items, int block, int per_sm) {
+  long long b = (work_items + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+int upload_head(const float* w, const float* b, int K, int cin, cudaStream_t st) {
+  if (cin != kHeadC || K <= 0 || K > kMaxK) {
+    set_error("head: needs cin == %d and 0 < classes <= %d (got %d, %d)", kHeadC, kMaxK, cin, K);
+    return SPFF_ERR_BAD_ARGUMENT;
+  }
+  SPFF_CUDA(cudaMemcpyToSymbolAsync(c_head_w, w, sizeof(float) * K * kHeadC, 0, cudaMemcpyDeviceToDevice, st));
+  if (b)
+    SPFF_CUDA(cudaMemcpyToSymbolAsync(c_head_b, b, sizeof(float) * K, 0, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+constexpr int kStemWgradBlocksPerSm = 2;
+constexpr int kHeadBwdBlocksPerSm = 2;
+
+}  // namespace
+}  // namespace spff
+
+#define SPFF_ENTRY_CHECK()        \
+  do {                            \
+    int _e = spff_device_check(); \
+    if (_e) return _e;            \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int spff_conv3d_stem_fwd(const float* x, const float* w, void* y, long long ldy, int cout, spff_shape s,
+                         void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(x && w && y && cout % 8 == 0 && cout > 0 && cout <= 256, "conv3d_stem_fwd: bad arguments (cout %d)", cout);
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w * (cout / 8);
+  const int grid = spff::grid_for(total, 256, 16);
+  spff::stem_fwd_kernel<<<grid, 256, 27 * cout * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      x, w, static_cast<bf16*>(y), ldy, cout, s);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t spff_conv3d_stem_wgrad_workspace(int cout) {
+  return static_cast<size_t>(spff::num_sms()) * spff::kStemWgradBlocksPerSm * 27 * cout * sizeof(float);
+}
+
+int spff_conv3d_stem_wgrad(const float* x, const void* dy, long long lddy, int cout, spff_shape s, float* dw,
+                           float beta, void* workspace, size_t workspace_bytes, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(x && dy && dw && workspace, "conv3d_stem_wgrad: null pointer");
+  SPFF_REQUIRE(cout == spff::kStemCo, "conv3d_stem_wgrad: cout must be %d (got %d)", spff::kStemCo, cout);
+  if (workspace_bytes < spff_conv3d_stem_wgrad_workspace(cout)) {
+    spff::set_error("conv3d_stem_wgrad: workspace too small");
+    return SPFF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = spff::num_sms() * spff::kStemWgradBlocksPerSm;
+  spff::stem_wgrad_kernel<<<blocks, 256, 8 * 27 * cout * sizeof(float), st>>>(x, static_cast<const bf16*>(dy), lddy,
+                                                                              cout, s, static_cast<float*>(workspace));
+  spff::stem_wgrad_reduce_kernel<<<(27 * cout + 127) / 128, 128, 0, st>>>(static_cast<const float*>(workspace), blocks,
+                                                                         cout, beta, dw);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_head_fwd(const void* x, long long ldx, int cin, const float* w, const float* b, float* logits, int k,
+                  spff_shape s, void* stream) {
+  SPFF_ENTRY_CHECK();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int e = spff::upload_head(w, b, k, cin, st);
+  if (e) return e;
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w;
+  spff::head_fwd_kernel<false><<<spff::grid_for(total, 256, 8), 256, 0, st>>>(
+      static_cast<const bf16*>(x), ldx, logits, nullptr, k, static_cast<long long>(s.d) * s.h * s.w, total);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_head_argmax(const void* x, long long ldx, int cin, const float* w, const float* b, uint8_t* labels, int k,
+                     spff_shape s, void* stream) {
+  SPFF_ENTRY_CHECK();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int e = spff::upload_head(w, b, k, cin, st);
+  if (e) return e;
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w;
+  spff::head_fwd_kernel<true><<<spff::grid_for(total, 256, 8), 256, 0, st>>>(
+      static_cast<const bf16*>(x), ldx, nullptr, labels, k, static_cast<long long>(s.d) * s.h * s.w, total);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t spff_head_bwd_workspace(int k) {
+  return static_cast<size_t>(spff::num_sms()) * spff::kHeadBwdBlocksPerSm * (k * spff::kHeadC + k) * sizeof(float);
+}
+
+int spff_head_bwd(const float* dlogits, const void* x, long long ldx, int cin, const float* w, void* dx,
+                  long long lddx, float* dw, float* db, float beta, int k, spff_shape s, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(dlogits && x && w && dw && db && workspace, "head_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int e = spff::upload_head(w, nullptr, k, cin, st);
+  if (e) return e;
+  if (workspace_bytes < spff_head_bwd_workspace(k)) {
+    spff::set_error("head_bwd: workspace too small");
+    return SPFF_ERR_WORKSPACE;
+  }
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w;
+  const int blocks = spff::num_sms() * spff::kHeadBwdBlocksPerSm;
+  const size_t smem = 8 * (spff::kMaxK * spff::kHeadC + spff::kMaxK) * sizeof(float);
+  spff::head_bwd_kernel<<<blocks, 256, smem, st>>>(dlogits, static_cast<const bf16*>(x), ldx, static_cast<bf16*>(dx),
+                                                  lddx, k, static_cast<long long>(s.d) * s.h * s.w, total,
+                                                  static_cast<float*>(workspace));
+  const int tot = k * spff::kHeadC + k;
+  spff::head_bwd_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(static_cast<const float*>(workspace), blocks, k, beta,
+                                                                 dw, db);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_ce_confusion(const float* logits, const void* labels, int label_bytes, int ignore_index, int k,
+                      spff_shape s, double* acc, long long* counts, long long* confusion, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(logits && labels && acc && counts && confusion, "ce_confusion: null pointer");
+  SPFF_REQUIRE(k > 0 && k <= spff::kMaxK, "ce_confusion: classes must be in 1..%d", spff::kMaxK);
+  SPFF_REQUIRE(label_bytes == 1 || label_bytes == 8, "ce_confusion: labels must be uint8 or int64");
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w;
+  const long long dhw = static_cast<long long>(s.d) * s.h * s.w;
+  const int grid = spff::grid_for(total, 256, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto cnt = reinterpret_cast<unsigned long long*>(counts);
+  auto conf = reinterpret_cast<unsigned long long*>(confusion);
+  if (label_bytes == 1)
+    spff::ce_kernel<uint8_t, false><<<grid, 256, 0, st>>>(logits, labels, ignore_index, k, dhw, total, acc, cnt, conf,
+                                                          nullptr, nullptr, nullptr);
+  else
+    spff::ce_kernel<long long, false><<<grid, 256, 0, st>>>(logits, labels, ignore_index, k, dhw, total, acc, cnt, conf,
+                                                            nullptr, nullptr, nullptr);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_ce_grad(const float* logits, const void* labels, int label_bytes, int ignore_index, int k, spff_shape s,
+                 const long long* n_valid, const float* gscale, float* dlogits, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(logits && labels && n_valid && dlogits, "ce_grad: null pointer");
+  SPFF_REQUIRE(k > 0 && k <= spff::kMaxK, "ce_grad: classes must be in 1..%d", spff::kMaxK);
+  SPFF_REQUIRE(label_bytes == 1 || label_bytes == 8, "ce_grad: labels must be uint8 or int64");
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w;
+  const long long dhw = static_cast<long long>(s.d) * s.h * s.w;
+  const int grid = spff::grid_for(total, 256, 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto nv = reinterpret_cast<const unsigned long long*>(n_valid);
+  if (label_bytes == 1)
+    spff::ce_kernel<uint8_t, true><<<grid, 256, 0, st>>>(logits, labels, ignore_index, k, dhw, total, nullptr, nullptr,
+                                                         nullptr, nv, gscale, dlogits);
+  else
+    spff::ce_kernel<long long, true><<<grid, 256, 0, st>>>(logits, labels, ignore_index, k, dhw, total, nullptr,
+                                                           nullptr, nullptr, nv, gscale, dlogits);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adam_step: bad arguments");
+  if (n == 0) return 0;
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  spff::adam_kernel<<<spff::grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -82,3 +82,181 @@ def conv3d_k3_wgrad(x, cin, dy, cout, dw, beta: float = 0.0, ws: torch.Tensor | 
         ws = conv3d_k3_wgrad_workspace(cin, cout, x)
     call("spff_conv3d_k3_wgrad", ptr(x), ldx, cin, ptr(dy), lddy, cout, s, ptr(dw), float(beta), ptr(ws),
          ws.numel(), stream_ptr())
+
+
+# ------------------------------------------------------------------------------------------------
+# stem / transposed conv
+# ------------------------------------------------------------------------------------------------
+def _shape5(x5):
+    n, _, d, h, w = x5.shape
+    return Shape(n, d, h, w)
+
+
+def conv3d_stem_fwd(x, w, y, cout):
+    """x fp32 [N,1,D,H,W] contiguous, w fp32 [cout,1,3,3,3] -> y bf16 view."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 1
+    s, ldy = _view(y, cout)
+    call("spff_conv3d_stem_fwd", ptr(x), ptr(w), ptr(y), ldy, cout, s, stream_ptr())
+
+
+def conv3d_stem_wgrad(x, dy, cout, dw, beta=0.0):
+    s, lddy = _view(dy, cout)
+    ws = workspace(int(_lib.lib.spff_conv3d_stem_wgrad_workspace(cout)), x.device)
+    call("spff_conv3d_stem_wgrad", ptr(x), ptr(dy), lddy, cout, s, ptr(dw), float(beta), ptr(ws), ws.numel(),
+         stream_ptr())
+
+
+def pack_convt_weight(w):
+    """nn.ConvTranspose3d weight [Cin,Cout,1,2,2] fp32 -> (w_fwd, w_dgrad) bf16."""
+    cin, cout = w.shape[0], w.shape[1]
+    w = w.detach().contiguous().float()
+    wf = torch.empty(4 * cin * cout, dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty(4 * cin * cout, dtype=torch.bfloat16, device=w.device)
+    call("spff_pack_convt_weight", ptr(w), ptr(wf), ptr(wd), cin, cout, stream_ptr())
+    return wf, wd
+
+
+def convt_k122_fwd(x, cin, w_fwd, bias, y, cout):
+    s, ldx = _view(x, cin)
+    s2, ldy = _view(y, cout)
+    assert (s2.h, s2.w) == (2 * s.h, 2 * s.w)
+    call("spff_convt_k122_fwd", ptr(x), ldx, cin, ptr(w_fwd), ptr(bias), ptr(y), ldy, cout, s, stream_ptr())
+
+
+def convt_k122_dgrad(dy, cout, w_dgrad, dx, cin):
+    s, lddx = _view(dx, cin)
+    s2, lddy = _view(dy, cout)
+    assert (s2.h, s2.w) == (2 * s.h, 2 * s.w)
+    call("spff_convt_k122_dgrad", ptr(dy), lddy, cout, ptr(w_dgrad), ptr(dx), lddx, cin, s, stream_ptr())
+
+
+def convt_k122_wgrad(x, cin, dy, cout, dw, beta=0.0):
+    s, ldx = _view(x, cin)
+    _, lddy = _view(dy, cout)
+    ws = workspace(int(_lib.lib.spff_convt_k122_wgrad_workspace(cin, cout, s)), x.device)
+    call("spff_convt_k122_wgrad", ptr(x), ldx, cin, ptr(dy), lddy, cout, s, ptr(dw), float(beta), ptr(ws), ws.numel(),
+         stream_ptr())
+
+
+# ------------------------------------------------------------------------------------------------
+# norm / act / SPFF tail
+# ------------------------------------------------------------------------------------------------
+def in_stats(x, c, stats):
+    """stats fp64 [N,C,2] += {sum, sum sq}."""
+    s, ldx = _view(x, c)
+    call("spff_in_stats", ptr(x), ldx, c, s, ptr(stats), stream_ptr())
+
+
+def in_coeffs(stats, gamma, beta, eps, n, c, count, coef, batch_stats=False):
+    call("spff_in_coeffs", ptr(stats), ptr(gamma), ptr(beta), float(eps), n, c, int(count), int(batch_stats), ptr(coef),
+         stream_ptr())
+
+
+def norm_act_apply(x, coef, y, c, slope):
+    s, ldx = _view(x, c)
+    _, ldy = _view(y, c)
+    call("spff_norm_act_apply", ptr(x), ldx, ptr(coef), ptr(y), ldy, c, s, float(slope), stream_ptr())
+
+
+def norm_act_reduce(x, coef, S, c, slope):
+    s, ldx = _view(x, c)
+    call("spff_norm_act_reduce", ptr(x), ldx, ptr(coef), ptr(S), c, s, float(slope), stream_ptr())
+
+
+def norm_act_affine_apply(x, coef, P, Q, y, ypool, c, slope):
+    s, ldx = _view(x, c)
+    _, ldy = _view(y, c)
+    ldp = _view(ypool, c)[1] if ypool is not None else 0
+    call("spff_norm_act_affine_apply", ptr(x), ldx, ptr(coef), ptr(P), ptr(Q), ptr(y), ldy, ptr(ypool), ldp, c, s,
+         float(slope), stream_ptr())
+
+
+def gate_micro_fwd(S, g1, bt, kfg, se, flags, c, shape, P, Q):
+    w1, b1, w2, b2 = se if se is not None else (None, None, None, None)
+    hid = w1.shape[0] if w1 is not None else 0
+    call("spff_gate_micro_fwd", ptr(S), ptr(g1), ptr(bt), ptr(kfg), ptr(w1), ptr(b1), ptr(w2), ptr(b2), hid, flags, c,
+         shape, ptr(P), ptr(Q), stream_ptr())
+
+
+def norm_act_bwd_reduce(dout, x, coef, R, c, slope):
+    s, lddo = _view(dout, c)
+    _, ldx = _view(x, c)
+    call("spff_norm_act_bwd_reduce", ptr(dout), lddo, ptr(x), ldx, ptr(coef), ptr(R), c, s, float(slope), stream_ptr())
+
+
+def gate_micro_bwd(R, S, coef, gamma, g1, bt, kfg, se, flags, c, shape, bcoef, dSa, Pout, dgamma, dbeta, dg1, dbt, dkfg,
+                   dse):
+    w1, b1, w2, b2 = se if se is not None else (None, None, None, None)
+    dw1, db1, dw2, db2 = dse if dse is not None else (None, None, None, None)
+    hid = w1.shape[0] if w1 is not None else 0
+    call("spff_gate_micro_bwd", ptr(R), ptr(S), ptr(coef), ptr(gamma), ptr(g1), ptr(bt), ptr(kfg), ptr(w1), ptr(b1),
+         ptr(w2), ptr(b2), hid, flags, c, shape, ptr(bcoef), ptr(dSa), ptr(Pout), ptr(dgamma), ptr(dbeta), ptr(dg1),
+         ptr(dbt), ptr(dkfg), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), stream_ptr())
+
+
+def norm_act_bwd_apply(dout, x, coef, bcoef, P, dSa, dx, c, slope):
+    s, lddo = _view(dout, c)
+    _, ldx = _view(x, c)
+    _, lddx = _view(dx, c)
+    call("spff_norm_act_bwd_apply", ptr(dout), lddo, ptr(x), ldx, ptr(coef), ptr(bcoef), ptr(P), ptr(dSa), ptr(dx), lddx,
+         c, s, float(slope), stream_ptr())
+
+
+def maxpool_bwd_add(dpool, y, dskip, c, accumulate):
+    s, ldy = _view(y, c)
+    _, ldp = _view(dpool, c)
+    _, ldd = _view(dskip, c)
+    call("spff_maxpool_bwd_add", ptr(dpool), ldp, ptr(y), ldy, ptr(dskip), ldd, c, s, int(accumulate), stream_ptr())
+
+
+# ------------------------------------------------------------------------------------------------
+# head / loss / optimizer
+# ------------------------------------------------------------------------------------------------
+def head_fwd(x, w, b, logits):
+    """x bf16 view (32 ch), w fp32 [K,32] (any trailing 1-dims), logits fp32 [N,K,D,H,W] contiguous."""
+    k = w.shape[0]
+    s, ldx = _view(x, 32)
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    call("spff_head_fwd", ptr(x), ldx, 32, ptr(w), ptr(b), ptr(logits), k, s, stream_ptr())
+
+
+def head_argmax(x, w, b, labels):
+    k = w.shape[0]
+    s, ldx = _view(x, 32)
+    assert labels.dtype == torch.uint8 and labels.is_contiguous()
+    call("spff_head_argmax", ptr(x), ldx, 32, ptr(w), ptr(b), ptr(labels), k, s, stream_ptr())
+
+
+def head_bwd(dlogits, x, w, dx, dw, db, beta=0.0):
+    k = w.shape[0]
+    s, ldx = _view(x, 32)
+    lddx = _view(dx, 32)[1] if dx is not None else 0
+    ws = workspace(int(_lib.lib.spff_head_bwd_workspace(k)), x.device)
+    call("spff_head_bwd", ptr(dlogits), ptr(x), ldx, 32, ptr(w), ptr(dx), lddx, ptr(dw), ptr(db), float(beta), k, s,
+         ptr(ws), ws.numel(), stream_ptr())
+
+
+def _label_bytes(labels):
+    if labels.dtype == torch.uint8:
+        return 1
+    if labels.dtype == torch.int64:
+        return 8
+    raise ValueError("labels must be uint8 or int64")
+
+
+def ce_confusion(logits, labels, ignore_index, acc, counts, confusion):
+    n, k, d, h, w = logits.shape
+    assert logits.is_contiguous() and labels.is_contiguous()
+    call("spff_ce_confusion", ptr(logits), ptr(labels), _label_bytes(labels), int(ignore_index), k, Shape(n, d, h, w),
+         ptr(acc), ptr(counts), ptr(confusion), stream_ptr())
+
+
+def ce_grad(logits, labels, ignore_index, n_valid, gscale, dlogits):
+    n, k, d, h, w = logits.shape
+    call("spff_ce_grad", ptr(logits), ptr(labels), _label_bytes(labels), int(ignore_index), k, Shape(n, d, h, w),
+         ptr(n_valid), ptr(gscale), ptr(dlogits), stream_ptr())
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    call("spff_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+         int(step), float(grad_scale), stream_ptr())
