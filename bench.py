@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Headline benchmark: SPFF-UNet bf16 training step, voxels/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md §8d "C2"): per GPU a synthetic batch 8x5x128^3 presented
+the way the reference's data pipeline presents a scan, one z-slice per sample: x [1024,1,5,128,128]
+fp32, labels [1024,5,128,128] int64 in 0..12 -> 83 886 080 voxels per GPU per step. One step =
+forward + ce_plus_macro_dice_loss + backward (+ NCCL gradient all-reduce for N > 1) + Adam step, through
+`LitSPCT_EFiLM_FourierGate.fit_step` (the reference-facing plugin surface of this tree).
+
+  value     voxels/s with the batch already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e       the same step fed from pinned HOST buffers (H2D of images + labels and D2H of the loss
+            inside the timed region)
+  roofline  the dominant kernel family (conv3 fprop kernel: forward + dgrad launches): algorithmic
+            FLOPs / CUDA-event time of those launches inside the timed steps, vs the measured
+            sustained bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference   the CPU restatement of the reference's path (oracle/, the same
+            torch CPU fp32 operator sequence the reference dispatches) timed on the host cores on
+            a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "spff-unet-spcct_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "SPFF-UNet train voxels/s"
+FLOP_PER_VOXEL_TRAIN = 2_448_192          # fwd + dgrad + wgrad dense contractions
+SAMPLES, FRAMES, H, W = 1024, 5, 128, 128  # per GPU
+NUM_CLASSES = 13
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_step_time(samples: int, reps: int, warmup: int, budget_s: float = 1e9):
+    """Times `reps` steps (fwd + loss + bwd, CPU fp32, all host threads) of the oracle port on
+    `samples` slices of the bench shape; returns (seconds per step list, threads)."""
+    import torch
+
+    from oracle import spff_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    p = O.det_weights(O.param_shapes("SPFF-UNet"), seed=42)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(samples, 1, FRAMES, H, W, generator=g)
+    lab = torch.randint(0, NUM_CLASSES, (samples, FRAMES, H, W), generator=g)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        O.loss_and_grads(p, x, lab, "SPFF-UNet")
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_start > budget_s and times:
+            break
+    return times, threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (its torch CPU fp32
+    operator sequence, restated in oracle/spff_oracle.py and pinned to the reference by
+    tests/golden) on the host cores. Rank 0 only; a step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    samples = 4
+    times, threads = cpu_step_time(samples, args.steps, args.warmup)
+    vox = samples * FRAMES * H * W
+    sec = sum(times) / len(times)
+    value = vox / sec
+    sample = f"{samples} of the {SAMPLES} slices [1,5,{H},{W}] per step, fp32, fwd+loss+bwd, {threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus: int):
+    return {
+        "workload": f"SPFF-UNet bf16 training step, synthetic batch 8x5x128^3 per GPU = x[{SAMPLES},1,{FRAMES},{H},{W}] "
+                    f"(BASELINE.json configs[1]; configs[2] for N>1)",
+        "samples_per_gpu": SAMPLES, "voxels_per_gpu_step": SAMPLES * FRAMES * H * W, "num_classes": NUM_CLASSES,
+        "step": "fwd + CE/Dice loss + bwd + grad all-reduce + Adam", "parallelism": f"dp{n_gpus}",
+        "l2": "working set per sample group >> 126 MB L2 (inputs larger than L2; no flush needed)",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from innovative3D import config as C
+    from spff_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N > 1 must be launched with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    samples = int(os.environ.get("SPFF_BENCH_SAMPLES", SAMPLES))
+    torch.manual_seed(42)
+    lit = dict((v[0], v[1]) for v in C.VARIANTS)["SPFF-UNet"]().to(dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(samples, 1, FRAMES, H, W, generator=g).pin_memory()
+    lab_host = torch.randint(0, NUM_CLASSES, (samples, FRAMES, H, W), generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    lab_dev = lab_host.to(dev)
+    vox = samples * FRAMES * H * W
+    loss_host = torch.zeros(1).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t) * 1e-3
+
+    def step_resident():
+        return lit.fit_step((x_dev, lab_dev))
+
+    def step_e2e():
+        out = lit.fit_step((x_host, lab_host))            # H2D of images + labels inside
+        loss_host.copy_(out["loss"].reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()         # the loss is on the host when the step ends
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    # ---- device-resident steps, with CUDA events around the conv3 launches (roofline) ----
+    clocks = ClockSampler(local)
+    clocks.start()
+    conv_names = {"spff_conv3d_k3_fwd", "spff_conv3d_k3_dgrad", "spff_conv3d_k3_wgrad"}
+    prof = _lib.Profile(select=lambda n: n in conv_names)
+    calls0 = _lib.CALLS
+    _lib.PROFILE = prof
+    sec = timed(step_resident, args.steps)
+    _lib.PROFILE = None
+    launches = _lib.CALLS - calls0
+    clk = clocks.stop()
+    conv = prof.summary()
+    # ---- end-to-end steps from pinned host memory ----
+    step_e2e()
+    sec_e2e = timed(step_e2e, args.steps)
+    # ---- one extra step with every call timed: breakdown by entry point ----
+    full = _lib.Profile()
+    _lib.PROFILE = full
+    step_resident()
+    _lib.PROFILE = None
+    brk = full.summary()
+    final_loss = float(loss_host[0])
+
+    if rank == 0:
+        peaks, peak_kind = load_peaks()
+        n_f, ms_f, fl_f = conv.get("spff_conv3d_k3_fwd", (0, 0.0, 0.0))
+        n_d, ms_d, fl_d = conv.get("spff_conv3d_k3_dgrad", (0, 0.0, 0.0))
+        n_w, ms_w, fl_w = conv.get("spff_conv3d_k3_wgrad", (0, 0.0, 0.0))
+        ach = (fl_f + fl_d) / max(ms_f + ms_d, 1e-9) * 1e3 / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        value = world * vox * args.steps / sec
+        total_ms = sum(v[1] for v in brk.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world),
+            "clocks": clk,
+            "e2e": {"value": world * vox * args.steps / sec_e2e, "unit": "voxels/s",
+                    "h2d_bytes_per_step": x_host.numel() * 4 + lab_host.numel() * 8, "d2h_bytes_per_step": 4,
+                    "ms_per_step": sec_e2e / args.steps * 1e3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "conv3_fprop_kernel (3x3x3 conv forward + dgrad launches)",
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "peak_kind": f"{peak_kind} sustained bf16 (kernel timed inside a long step)",
+                         "launches": n_f + n_d, "ms_per_step": (ms_f + ms_d) / args.steps,
+                         "wgrad": {"achieved": fl_w / max(ms_w, 1e-9) * 1e3 / 1e12, "ms_per_step": ms_w / args.steps,
+                                   "launches": n_w},
+                         "step_tensor_frac": value / world * FLOP_PER_VOXEL_TRAIN / 1e12 / peak},
+            "breakdown_ms": {k: round(v[1], 3) for k, v in sorted(brk.items(), key=lambda kv: -kv[1][1])},
+            "breakdown_total_ms": round(total_ms, 3),
+            "final_loss": final_loss,
+        }
+        if not args.no_cpu and world >= 1:
+            t0 = time.perf_counter()
+            cs = 2
+            times, threads = cpu_step_time(cs, reps=3, warmup=1, budget_s=40.0)
+            cpu_sec = min(times)
+            line["cpu_baseline"] = {
+                "value": cs * FRAMES * H * W / cpu_sec, "unit": "voxels/s", "cores": threads, "kind": "port",
+                "sample": f"{cs} of the {samples} slices [1,5,{H},{W}] per step, fp32 fwd+loss+bwd, best of {len(times)} "
+                          f"({time.perf_counter() - t0:.0f} s of CPU work)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

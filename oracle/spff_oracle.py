@@ -239,16 +239,17 @@ def ce_plus_macro_dice_loss(logits: torch.Tensor, labels: torch.Tensor, num_clas
     return ce + 0.5 * (1.0 - macro_dice_from_confusion(cm, smooth))
 
 
-def metrics_from_confusion(cm: np.ndarray, n_valid: int | None = None, smooth: float = 1e-6):
+def metrics_from_confusion(cm: np.ndarray, total_voxels: int | None = None, smooth: float = 1e-6):
     """per_class_metrics_3d (helpers.py:668-725) from the [label][pred] tally: the 9-tuple
     (dice_list, sens_list, spec_list, macro_dice, macro_sens, macro_spec, micro_dice, micro_sens,
     micro_spec) with the reference's NaN rules (:693-701) and nanmean over classes 1.. (:708-710).
-    `n_valid` = number of voxels with label != ignore (defaults to cm.sum(); differs only if labels
-    outside [0,K) exist, which the reference would count in tn)."""
+    `total_voxels` = ALL voxels, ignored ones included: the reference's tn is
+    `(~pred_c & ~label_c).sum()` where both masks are already cleared on ignored voxels (:684-690),
+    so an ignored voxel is a true negative of every class (pinned by tests/golden case0/case4)."""
     import warnings
 
     k = cm.shape[0]
-    total = int(cm.sum()) if n_valid is None else int(n_valid)
+    total = int(cm.sum()) if total_voxels is None else int(total_voxels)
     dice_l: List[float] = []; sens_l: List[float] = []; spec_l: List[float] = []
     for c in range(k):
         tp = int(cm[c, c]); fp = int(cm[:, c].sum() - tp); fn = int(cm[c, :].sum() - tp)
@@ -277,8 +278,7 @@ def metrics_from_confusion(cm: np.ndarray, n_valid: int | None = None, smooth: f
 
 def per_class_metrics_3d(logits, labels, num_classes, smooth=1e-6, ignore_index=None):
     cm = confusion(torch.argmax(logits, dim=1), labels, num_classes, ignore_index)
-    n_valid = int((labels != ignore_index).sum()) if ignore_index is not None else labels.numel()
-    return metrics_from_confusion(cm, n_valid, smooth)
+    return metrics_from_confusion(cm, labels.numel(), smooth)
 
 
 # ------------------------------------------------------------------------------------------------

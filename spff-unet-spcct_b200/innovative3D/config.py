@@ -1,0 +1,102 @@
+"""Constants and the `VARIANTS` plugin registry of the hot path.
+
+Mirrors the part of the reference's `innovative3D/config.py` that the callers of the hot path
+import (`train.py:64-78,89`, `test.py:62-72`): the label space, the training constants
+(config.py:21-33) and `VARIANTS` — a list of `(name, zero-arg builder, DataModule, ckpt_dir)`
+(config.py:271-280) whose builders construct the Lightning modules of `innovative3D.models`
+(config.py:410-476). Dataset geometry (ROI tables, DICOM roots, config.py:36-124) is outside the
+hot path and not restated here; unlike the reference, importing this module creates no directories
+under a hard-coded home path (config.py:15-19) — only CHECKPOINT_DIR / LOG_DIR, both overridable
+through the same environment variables (config.py:252-253).
+"""
+import inspect
+import os
+from importlib import import_module
+from pathlib import Path
+
+IMAGE_HEIGHT, IMAGE_WIDTH = 512, 512   # config.py:21
+NUM_FRAMES = 5                         # config.py:22
+NUM_CLASSES = 13                       # config.py:23
+FINAL_EPOCHS = 200
+BEST_LR = 1e-4                         # config.py:25
+IGNORE_INDEX = 255                     # config.py:26
+BATCH_SIZE = 1                         # config.py:27
+NUM_WORKERS = 16
+num_workers = NUM_WORKERS
+grid_size = 10
+SEEDS = [42, 123, 999]                 # config.py:33
+
+global_label_names = {
+    0: "BG", 1: "HA800", 2: "HA400", 3: "HA200", 4: "HA100", 5: "Lung", 6: "Liver", 7: "Adipose",
+    8: "Water", 9: "I15", 10: "I10", 11: "I5", 12: "HA50",
+}
+label_colors = {
+    0: (0, 0, 0), 1: (255, 0, 0), 2: (255, 127, 0), 3: (255, 255, 0), 4: (0, 255, 0), 5: (0, 255, 255),
+    6: (0, 0, 255), 7: (139, 69, 19), 8: (255, 255, 255), 9: (255, 0, 255), 10: (128, 0, 128),
+    11: (0, 128, 128), 12: (128, 128, 0),
+}
+
+# Dataset selection lives with the data pipeline (out of scope); callers that import these names get
+# empty lists unless a data layer fills them.
+dataset_configs = []
+trainval_sets = []
+test_set = []
+
+LOSS_NAME = "ce_plus_macro_dice"
+FOCAL_ALPHA, FOCAL_GAMMA, GRAD_WEIGHT = 0.25, 2.0, 1.0
+USE_VMI = False
+
+_PROJECT_ROOT = Path(__file__).resolve().parents[1]
+CHECKPOINT_DIR = Path(os.getenv("CHECKPOINT_DIR", str(_PROJECT_ROOT / "runs" / "checkpoints"))).resolve()
+LOG_DIR = Path(os.getenv("LOG_DIR", str(_PROJECT_ROOT / "runs"))).resolve()
+CKPT_DIR = CHECKPOINT_DIR
+
+
+def MultiDicomDataModule3D(*args, **kwargs):
+    """The reference's DICOM data module (datasets.py:280-364) is the caller's side of the
+    boundary; resolve it lazily from whatever `innovative3D.datasets` is importable."""
+    try:
+        mod = import_module("innovative3D.datasets")
+    except ImportError as e:  # pragma: no cover - data layer is out of scope here
+        raise ImportError("innovative3D.datasets (the reference's CPU data pipeline) is not part of the B200 hot "
+                          "path; install the reference's data layer next to this package to train on DICOM data") from e
+    return mod.MultiDicomDataModule3D(*args, **kwargs)
+
+
+def build_class(class_name: str, **ctor_kwargs):
+    """Zero-arg factory for `innovative3D.models.<class_name>`, passing only the kwargs its
+    constructor accepts (same contract as config.py:159-182)."""
+    def _factory():
+        cls = getattr(import_module("innovative3D.models"), class_name, None)
+        if cls is None:
+            raise ImportError(f"[config] {class_name} not found in innovative3D.models")
+        params = inspect.signature(cls.__init__).parameters
+        if any(p.kind == inspect.Parameter.VAR_KEYWORD for p in params.values()):
+            return cls(**ctor_kwargs)
+        return cls(**{k: v for k, v in ctor_kwargs.items() if k in params})
+    return _factory
+
+
+VARIANTS = []
+
+
+def _add_variant(name, builder_or_class, dm_cls, ckpt_dir):
+    VARIANTS.append((name, builder_or_class, dm_cls, Path(ckpt_dir)))
+
+
+# shared constructor arguments of the SPCT family (config.py:410-419)
+_SPCT_COMMON = dict(num_classes=NUM_CLASSES, lr=BEST_LR, base=32, ksd=3, use_se=True, use_specse=True,
+                    use_spatial=False, use_skip_gate=False)
+
+_add_variant("SPFF-UNet", build_class("LitSPCT_EFiLM_FourierGate", **_SPCT_COMMON), MultiDicomDataModule3D,
+             CHECKPOINT_DIR / "SPFF-UNet")                                         # config.py:423-428
+_add_variant("E_SP_UNet", build_class("LitSPCT_EnergyFiLM", **_SPCT_COMMON), MultiDicomDataModule3D,
+             CHECKPOINT_DIR / "E_SP_UNet")                                         # config.py:433-438
+_add_variant("FG_SP_UNet", build_class("LitSPCT_FourierGate", **_SPCT_COMMON), MultiDicomDataModule3D,
+             CHECKPOINT_DIR / "FG_SP_UNet")                                        # config.py:443-448
+_add_variant("PlainCore_UNet",
+             build_class("LitSPCT_ControlUNet", **{**_SPCT_COMMON, "use_se": False, "use_specse": False}),
+             MultiDicomDataModule3D, CHECKPOINT_DIR / "PlainCore_UNet")            # config.py:460-476
+
+VARIANT_NAMES = [v[0] for v in VARIANTS]
+SELECTED_VARIANT = os.getenv("INNOVATIVE3D_VARIANT")

@@ -1,0 +1,534 @@
+"""SPCT-family network modules and Lightning wrappers — the reference's `innovative3D/models.py`
+surface for the hot path, executed by the B200 engine.
+
+Kept from the reference, name for name, so that `config.VARIANTS`, `train.py` and `test.py` work
+unchanged: the constructor signatures, the `.model` attribute, the parameter names / shapes /
+initialisation order (a checkpoint of either implementation loads into the other, and the same seed
+gives bit-identical initial weights), `forward(x) -> logits [B,K,F,H,W]`, `compute_loss`,
+`training_step / validation_step / test_step`, `configure_optimizers`, the logged metric names.
+
+What differs is below `UNet3D_SpectralCore.forward`: the reference walks its sub-modules and
+dispatches ~1500 ATen / cuDNN / cuFFT calls per step; here the sub-modules are
+parameter containers and the whole graph — forward, and backward through one autograd node — is
+scheduled by `spff_b200.engine.SpffEngine` onto libspff_b200.so. There is no eager fallback: on
+anything but an sm_100 device `forward` raises.
+
+In scope: LitSPCT_EFiLM_FourierGate ("SPFF-UNet"), LitSPCT_EnergyFiLM, LitSPCT_FourierGate,
+LitSPCT_ControlUNet ("PlainCore_UNet"). Options of the reference core that no in-scope variant turns on
+(`use_spatial`, `use_skip_gate`, `ksd != 3`, non-instance norms, `use_moe`) raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+try:  # the real Lightning when it is installed (the reference pins 2.6.1, requirements.txt:70)
+    import pytorch_lightning as pl
+except ImportError:  # not in this image: a minimal stand-in with the same method names
+    from ._lightning import pl
+
+from spff_b200 import ops
+from spff_b200.engine import LossTally, NetConfig, SpffEngine
+
+from .config import BEST_LR, IGNORE_INDEX, NUM_CLASSES, NUM_FRAMES
+from .helpers import (LOSS_REGISTRY, ce_plus_macro_dice_loss, metrics_from_confusion, per_class_metrics_2d,
+                      per_class_metrics_3d)
+
+LOG_PER_CLASS = os.getenv("LOG_PER_CLASS", "1") == "1"
+# samples per group of the engine's schedule (activations of one group live at a time in fit_step)
+SAMPLE_GROUP = int(os.getenv("SPFF_SAMPLE_GROUP", "32"))
+
+
+def _pick_first_if_seq(x):
+    return x[0] if isinstance(x, (list, tuple)) else x
+
+
+def _canonicalize_targets_2d(lbls):
+    """(B,F,H,W) -> max over frames; (H,W) -> (1,H,W); long (models.py:58-66)."""
+    lbls = _pick_first_if_seq(lbls)
+    if not torch.is_tensor(lbls):
+        lbls = torch.as_tensor(lbls)
+    if lbls.ndim == 4:
+        lbls = lbls.max(dim=1).values
+    elif lbls.ndim == 2:
+        lbls = lbls.unsqueeze(0)
+    return lbls.long()
+
+
+def _canonicalize_targets_3d(lbls):
+    """Normalise labels to (B,F,H,W) long (models.py:68-83)."""
+    lbls = _pick_first_if_seq(lbls)
+    if not torch.is_tensor(lbls):
+        lbls = torch.as_tensor(lbls)
+    if lbls.ndim == 5 and lbls.size(1) == 1:
+        lbls = lbls[:, 0]
+    if lbls.ndim == 5 and lbls.size(-1) == 1:
+        lbls = lbls[..., 0]
+    if lbls.ndim == 3:
+        lbls = lbls.unsqueeze(0)
+    assert lbls.ndim == 4, f"Need (B,F,H,W) labels, got {tuple(lbls.shape)}"
+    return lbls.long()
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers (same attribute names and construction order as the reference modules)
+# --------------------------------------------------------------------------------------------------
+class _EngineOwned(nn.Module):
+    """Sub-modules hold parameters; their math runs inside the fused engine schedule."""
+
+    def forward(self, *a, **kw):
+        raise RuntimeError(f"{type(self).__name__} is executed by the B200 engine as part of "
+                           "UNet3D_SpectralCore.forward; it has no stand-alone eager path")
+
+
+def _norm3d(c: int, kind: str = "instance") -> nn.Module:
+    if not (kind or "instance").lower().startswith("inst"):
+        raise NotImplementedError("only norm='instance' is on the B200 hot path (models.py:168-173)")
+    return nn.InstanceNorm3d(c, affine=True, eps=1e-5)
+
+
+def _act(kind: str = "lrelu") -> nn.Module:
+    if not (kind or "lrelu").lower().startswith("lrel"):
+        raise NotImplementedError("only act='lrelu' is on the B200 hot path (models.py:175-181)")
+    return nn.LeakyReLU(1e-2, inplace=True)
+
+
+def _conv3x3xk(cin, cout, ksd=1, bias=False):
+    if ksd != 3 or bias:
+        raise NotImplementedError("the B200 conv kernels implement the (3,3,3), bias-free convolution the SPCT "
+                                  "variants use (ksd=3, config.py:414)")
+    return nn.Conv3d(cin, cout, kernel_size=(3, 3, 3), padding=(1, 1, 1), bias=False)
+
+
+class _SEChannelLite(_EngineOwned):
+    """Channel squeeze-excite, hidden max(4, c // r) (models.py:600-609)."""
+
+    def __init__(self, c, r=16):
+        super().__init__()
+        h = max(4, c // r)
+        self.pool = nn.AdaptiveAvgPool3d(1)
+        self.fc = nn.Sequential(nn.Conv3d(c, h, 1, bias=True), nn.ReLU(inplace=True),
+                                nn.Conv3d(h, c, 1, bias=True), nn.Sigmoid())
+
+
+class _SpectralSE(_EngineOwned):
+    """x * sigmoid(mean over (C,H,W)) per energy bin (models.py:611-614); parameter free."""
+
+
+class _DoubleConvSpectral(_EngineOwned):
+    """conv-IN-LReLU twice (models.py:620-625)."""
+
+    def __init__(self, cin, cout, ksd=1, norm="instance", act="lrelu"):
+        super().__init__()
+        self.b1 = nn.Sequential(_conv3x3xk(cin, cout, ksd, bias=False), _norm3d(cout, norm), _act(act))
+        self.b2 = nn.Sequential(_conv3x3xk(cout, cout, ksd, bias=False), _norm3d(cout, norm), _act(act))
+
+
+class EnergyFiLM3D(_EngineOwned):
+    """Per-energy-bin FiLM: (gamma, beta) from a 1x1 Conv1d MLP over a sinusoidal code of the bin
+    index (models.py:1479-1512). Input independent -> evaluated once per step as a [C,F] table
+    (spff_b200.tables.efilm_tables)."""
+
+    def __init__(self, channels: int, hidden: int = 32, pe_dims: int = 16):
+        super().__init__()
+        self.channels = int(channels)
+        self.pe_dims = int(pe_dims)
+        self.mlp = nn.Sequential(nn.Conv1d(self.pe_dims, hidden, 1, bias=True), nn.ReLU(inplace=True),
+                                 nn.Conv1d(hidden, 2 * self.channels, 1, bias=True))
+
+
+class FourierGate3D(_EngineOwned):
+    """Gate over the energy axis through a learnable rFFT magnitude mask (models.py:1515-1544).
+    Like the reference, `freq_mask` ([1,1,F//2+1,1,1], ones) is registered lazily at the first
+    forward (models.py:1532-1535) — so it is absent from a fresh module's state_dict and from an
+    optimizer built before the first forward. `learn_phase=True` is not on the hot path."""
+
+    def __init__(self, learn_phase: bool = False):
+        super().__init__()
+        if learn_phase:
+            raise NotImplementedError("FourierGate3D(learn_phase=True) is not used by any in-scope variant")
+        self.learn_phase = False
+        self.mag_scale = nn.Parameter(torch.ones(1))
+        self._mask = None
+
+    def ensure_mask(self, frames: int, device) -> bool:
+        """Register (or re-register when F changes) the lazy mask; True if a new parameter was made."""
+        length = frames // 2 + 1
+        if self._mask is not None and self._mask.shape[2] == length:
+            return False
+        self._mask = nn.Parameter(torch.ones(1, 1, length, 1, 1, device=device, dtype=torch.float32))
+        self.register_parameter("freq_mask", self._mask)
+        return True
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # a checkpoint saved after the first forward carries freq_mask: make room for it
+        key = prefix + "freq_mask"
+        if key in state_dict and (self._mask is None or self._mask.shape != state_dict[key].shape):
+            self._mask = nn.Parameter(torch.ones_like(state_dict[key], dtype=torch.float32,
+                                                      device=self.mag_scale.device))
+            self.register_parameter("freq_mask", self._mask)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class _DoubleConvSpectral_Novel(_EngineOwned):
+    """conv-IN-LReLU twice + EnergyFiLM + FourierGate (models.py:1448-1478)."""
+
+    def __init__(self, cin, cout, ksd=1, norm="instance", act="lrelu", use_efilm: bool = False,
+                 use_fouriergate: bool = False, use_moe: bool = False, moe_K: int = 3):
+        super().__init__()
+        if use_moe:
+            raise NotImplementedError("use_moe refers to SpectralMoE3D, which the reference does not define "
+                                      "(models.py:1464)")
+        self.pre = nn.Sequential(_conv3x3xk(cin, cout, ksd, bias=False), _norm3d(cout, norm), _act(act))
+        self.body = nn.Sequential(_conv3x3xk(cout, cout, ksd, bias=False), _norm3d(cout, norm), _act(act))
+        self.efilm = EnergyFiLM3D(cout) if use_efilm else nn.Identity()
+        self.fgate = FourierGate3D() if use_fouriergate else nn.Identity()
+
+
+class _CoreFn(torch.autograd.Function):
+    """The whole network as one autograd node: forward keeps the engine's saved activations,
+    backward returns the gradient of every parameter (none for the images)."""
+
+    @staticmethod
+    def forward(ctx, x, core, *params):
+        logits, state = core.engine.forward_saved(x, group=core.sample_group)
+        ctx.core, ctx.state = core, state
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        core = ctx.core
+        flat = torch.zeros(core._flat_numel, device=dlogits.device)
+        G = core._views(flat)
+        core.engine.backward_saved(ctx.state, dlogits, G)
+        ctx.state = None
+        return (None, None) + tuple(G[n] for n in core._names)
+
+
+class UNet3D_SpectralCore(nn.Module):
+    """Depth-preserving 4-level U-Net over [B,1,F,H,W] (models.py:647-701): pooling / upsampling in
+    (H,W) only, 3x3x3 convs mixing the energy bins, optional Channel-SE + Spectral-SE after every
+    encoder stage. Same constructor as the reference; H and W must be multiples of 8."""
+
+    def __init__(self, in_channels=1, num_classes=2, base=32, ksd=3, use_se=False, use_specse=False,
+                 use_spatial=False, use_skip_gate=False, norm="instance", act="lrelu"):
+        super().__init__()
+        if in_channels != 1:
+            raise NotImplementedError("the SPCT family feeds energy bins on the depth axis: in_channels=1 (models.py:1551)")
+        if int(base) != 32:
+            raise NotImplementedError("the B200 kernels are built for base=32 (config.py:413)")
+        if use_spatial or use_skip_gate:
+            raise NotImplementedError("use_spatial / use_skip_gate are off in every in-scope variant (config.py:416-418)")
+        if not 0 < num_classes <= 16:
+            raise NotImplementedError("the head / loss kernels support up to 16 classes")
+        f = int(base)
+        P = (1, 2, 2)
+        self.enc1 = _DoubleConvSpectral(in_channels, f, ksd, norm, act)
+        self.pool1 = nn.MaxPool3d(P)
+        self.enc2 = _DoubleConvSpectral(f, 2 * f, ksd, norm, act)
+        self.pool2 = nn.MaxPool3d(P)
+        self.enc3 = _DoubleConvSpectral(2 * f, 4 * f, ksd, norm, act)
+        self.pool3 = nn.MaxPool3d(P)
+        self.bott = _DoubleConvSpectral(4 * f, 8 * f, ksd, norm, act)
+        self.up3 = nn.ConvTranspose3d(8 * f, 4 * f, kernel_size=P, stride=P)
+        self.dec3 = _DoubleConvSpectral(8 * f, 4 * f, ksd, norm, act)
+        self.up2 = nn.ConvTranspose3d(4 * f, 2 * f, kernel_size=P, stride=P)
+        self.dec2 = _DoubleConvSpectral(4 * f, 2 * f, ksd, norm, act)
+        self.up1 = nn.ConvTranspose3d(2 * f, f, kernel_size=P, stride=P)
+        self.dec1 = _DoubleConvSpectral(2 * f, f, ksd, norm, act)
+        self.out = nn.Conv3d(f, num_classes, 1)
+        self.se = nn.ModuleList([_SEChannelLite(c) if use_se else nn.Identity() for c in (f, 2 * f, 4 * f, 8 * f)])
+        self.sp = nn.ModuleList([_SpectralSE() if use_specse else nn.Identity() for _ in range(4)])
+        self.sa = nn.ModuleList([nn.Identity() for _ in range(4)])
+        self.g3 = self.g2 = self.g1 = None
+        self._num_classes, self._base = int(num_classes), f
+        self._use_se, self._use_specse = bool(use_se), bool(use_specse)
+        self.sample_group = SAMPLE_GROUP
+        self._engine: Optional[SpffEngine] = None
+        self._flat: Optional[torch.Tensor] = None
+        self._names: List[str] = []
+        self._slots: Dict[str, tuple] = {}
+        self._flat_numel = 0
+        self._n_eager = 0     # elements of the flat buffer that existed before any lazy registration
+
+    # -- structure -----------------------------------------------------------------------------
+    def net_config(self) -> NetConfig:
+        blk = self.enc1
+        novel = isinstance(blk, _DoubleConvSpectral_Novel)
+        return NetConfig(num_classes=self._num_classes, base=self._base,
+                         conv_names=("pre", "body") if novel else ("b1", "b2"),
+                         efilm=novel and isinstance(blk.efilm, EnergyFiLM3D),
+                         fgate=novel and isinstance(blk.fgate, FourierGate3D),
+                         specse=self._use_specse, chanse=self._use_se)
+
+    @property
+    def engine(self) -> SpffEngine:
+        if self._engine is None:
+            self._engine = SpffEngine(self.net_config(), lambda: self._param_data,
+                                      lambda: tuple(p._version for p in self._param_objs.values()))
+        return self._engine
+
+    # -- flat parameter storage ------------------------------------------------------------------
+    def _views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {n: flat[o:o + k].view(shape) for n, (o, k, shape) in self._slots.items()}
+
+    def materialize(self, frames: int = NUM_FRAMES):
+        """Register the lazy FourierGate masks for `frames` bins and (re)build the flat fp32 parameter
+        buffer: every parameter's `.data` becomes a view of it (names, shapes and values unchanged),
+        so the gradient all-reduce and the fused Adam run over one contiguous range. The lazily
+        registered masks sit at the tail of the buffer, after `self._n_eager` elements."""
+        dev = self.out.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("UNet3D_SpectralCore (B200 build) must live on a CUDA sm_100 device: there is no CPU "
+                               "fallback. Call .to('cuda') / .cuda() first.")
+        for m in self.modules():
+            if isinstance(m, FourierGate3D):
+                m.ensure_mask(frames, dev)
+        # named_parameters() de-duplicates the two aliases of a lazy mask and yields `fgate._mask`
+        # (the attribute assignment registers first, as in the reference); the engine and the flat
+        # buffer use the public name `fgate.freq_mask`
+        named = [(n.replace("fgate._mask", "fgate.freq_mask"), p) for n, p in self.named_parameters()]
+        ok = self._flat is not None and self._flat.device == dev and len(named) == len(self._names)
+        if ok:
+            base, end = self._flat.data_ptr(), self._flat.data_ptr() + 4 * self._flat_numel
+            ok = all(base <= p.data_ptr() < end and p.dtype == torch.float32 for _, p in named)
+        if ok:
+            return
+        eager = [(n, p) for n, p in named if not n.endswith("freq_mask")]
+        lazy = [(n, p) for n, p in named if n.endswith("freq_mask")]
+        slots, off = {}, 0
+        for n, p in eager + lazy:
+            k = p.numel()
+            slots[n] = (off, k, tuple(p.shape))
+            off += (k + 3) // 4 * 4          # 16-byte aligned slices
+            if n == eager[-1][0]:
+                self._n_eager = off
+        flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for n, p in eager + lazy:
+            o, k, shape = slots[n]
+            v = flat[o:o + k].view(shape)
+            v.copy_(p.data)
+            p.data = v
+        self._flat, self._slots, self._flat_numel = flat, slots, off
+        self._names = [n for n, _ in named]
+        self._param_objs = dict(named)
+        self._param_data = {n: p.data for n, p in named}
+        if self._engine is not None:
+            self._engine.invalidate_weights()
+
+    # -- forward ---------------------------------------------------------------------------------
+    def forward(self, x):
+        x = _pick_first_if_seq(x)
+        if x.ndim == 4:
+            x = x.unsqueeze(1)
+        self.materialize(x.shape[2])
+        x = x.to(self.out.weight.device)
+        params = [self._param_objs[n] for n in self._names]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _CoreFn.apply(x, self, *params)
+        return self.engine.infer(x, group=self.sample_group)
+
+    @torch.no_grad()
+    def predict_labels(self, x) -> torch.Tensor:
+        """uint8 label map [B,F,H,W] = argmax over classes, fused into the head kernel (the label
+        maps `test.py:710-722` derives from softmax + argmax on the host)."""
+        x = _pick_first_if_seq(x)
+        self.materialize(x.shape[2])
+        return self.engine.infer(x.to(self.out.weight.device), group=self.sample_group, argmax=True)
+
+
+def upgrade_spct_with_novel_blocks(m: nn.Module, use_efilm: bool = True, use_fouriergate: bool = True,
+                                   use_moe: bool = False, moe_K: int = 3):
+    """Replace every `_DoubleConvSpectral` child by the novel block, keeping channels
+    (models.py:1416-1446). New blocks are constructed in `named_children` order like the
+    reference, so a seeded construction draws the same initial weights."""
+    for name, child in list(m.named_children()):
+        if isinstance(child, _DoubleConvSpectral):
+            conv1, conv2 = child.b1[0], child.b2[0]
+            setattr(m, name, _DoubleConvSpectral_Novel(int(conv1.in_channels), int(conv2.out_channels),
+                                                       ksd=int(conv1.kernel_size[0]), use_efilm=use_efilm,
+                                                       use_fouriergate=use_fouriergate, use_moe=use_moe, moe_K=moe_K))
+        else:
+            upgrade_spct_with_novel_blocks(child, use_efilm, use_fouriergate, use_moe, moe_K)
+    if isinstance(m, UNet3D_SpectralCore):
+        m._engine = None
+    return m
+
+
+def build_spct_energyfilm_fourier(num_classes=NUM_CLASSES, base=32, ksd=3, use_se=True, use_specse=True,
+                                  use_spatial=False, use_skip_gate=False, **kw):
+    """models.py:1547-1555."""
+    core = UNet3D_SpectralCore(in_channels=1, num_classes=num_classes, base=base, ksd=ksd, use_se=use_se,
+                               use_specse=use_specse, use_spatial=use_spatial, use_skip_gate=use_skip_gate, **kw)
+    return upgrade_spct_with_novel_blocks(core, use_efilm=True, use_fouriergate=True, use_moe=False)
+
+
+# --------------------------------------------------------------------------------------------------
+# Lightning wrappers
+# --------------------------------------------------------------------------------------------------
+class BaseLitModel(pl.LightningModule):
+    """Step driver (models.py:466-594): forward, ce_plus_macro_dice_loss, per-step metrics, Adam +
+    ReduceLROnPlateau on `val_macro_dice`. `fit_step` is the B200-native fused equivalent of
+    Lightning's training_step + backward + optimizer step."""
+
+    def __init__(self, num_classes=NUM_CLASSES, lr=BEST_LR, is_3d=True, **kwargs):
+        super().__init__()
+        self.is_3d = bool(is_3d)
+        self.save_hyperparameters({"num_classes": num_classes, "lr": float(lr), "is_3d": bool(is_3d), **kwargs})
+        self._fused = None
+
+    def _normalize_input(self, x):
+        return _pick_first_if_seq(x)
+
+    def forward(self, x):
+        return self.model(self._normalize_input(x))
+
+    def compute_loss(self, logits, labels):
+        return ce_plus_macro_dice_loss(logits, labels, self.hparams.num_classes, ignore_index=IGNORE_INDEX)
+
+    def _log_metrics(self, prefix, loss, metrics):
+        (dice_list, sens_list, spec_list, macro_dice, macro_sens, macro_spec, micro_dice, micro_sens,
+         micro_spec) = metrics
+        kw = dict(on_step=False, on_epoch=True, sync_dist=True)
+        self.log(f"{prefix}_loss", loss, prog_bar=(prefix == "train"), **kw)
+        self.log(f"{prefix}_macro_dice", macro_dice, prog_bar=(prefix != "test"), **kw)
+        for name, v in (("micro_dice", micro_dice), ("macro_sens", macro_sens), ("macro_spec", macro_spec),
+                        ("micro_sens", micro_sens), ("micro_spec", micro_spec)):
+            self.log(f"{prefix}_{name}", v, prog_bar=True, **kw)
+        for i, (d, s, sp) in enumerate(zip(dice_list, sens_list, spec_list)):
+            self.log(f"{prefix}_dice_class_{i}", d, prog_bar=False, **kw)
+            self.log(f"{prefix}_sens_class_{i}", s, prog_bar=False, **kw)
+            self.log(f"{prefix}_spec_class_{i}", sp, prog_bar=False, **kw)
+
+    def _shared_step(self, batch, prefix):
+        """models.py:479-586 without the test-only sklearn PR/ROC curves (CPU post-processing the
+        reference's own test pass in train.py:676-878 repeats; outside the hot path)."""
+        imgs, lbls = batch if isinstance(batch, (list, tuple)) else (batch["image"], batch["label"])
+        imgs = _pick_first_if_seq(imgs)
+        lbls = _pick_first_if_seq(lbls)
+        if not self.is_3d:
+            lbls = _canonicalize_targets_2d(lbls)
+        logits = self(imgs)
+        lbls = lbls.to(logits.device).long()
+        loss = self.compute_loss(logits, lbls)
+        fn = per_class_metrics_3d if self.is_3d else per_class_metrics_2d
+        self._log_metrics(prefix, loss, fn(logits, lbls, self.hparams.num_classes, ignore_index=IGNORE_INDEX))
+        return loss
+
+    def training_step(self, batch, batch_idx, dataloader_idx=0):
+        return self._shared_step(batch, "train")
+
+    def validation_step(self, batch, batch_idx, dataloader_idx=0):
+        return {"val_loss": self._shared_step(batch, "val")}
+
+    def test_step(self, batch, batch_idx):
+        return self._shared_step(batch, "test")
+
+    def configure_optimizers(self):
+        opt = torch.optim.Adam(self.parameters(), lr=self.hparams.lr)
+        sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="max", factor=0.5, patience=5)
+        return {"optimizer": opt, "lr_scheduler": {"scheduler": sch, "monitor": "val_macro_dice"}}
+
+    # -- B200-native fused training step ---------------------------------------------------------
+    def fit_step(self, batch, optimize: bool = True, sample_group: Optional[int] = None):
+        """forward + ce_plus_macro_dice_loss + backward (+ data-parallel gradient all-reduce + Adam
+        step) in the engine's sample-group schedule, without materialising the batch's activations
+        or logits. Equivalent to `loss = training_step(batch); loss.backward(); optimizer.step()` with
+        `torch.optim.Adam(lr=hparams.lr)`; like the reference (models.py:1532-1535 + :591-594) the
+        lazily registered `freq_mask` parameters receive gradients but are not stepped.
+
+        Under torch.distributed (one process per GPU) every rank passes its own shard of the batch;
+        gradients are summed with ONE NCCL all-reduce over the flat buffer and scaled by 1/world in
+        the Adam kernel — DistributedDataParallel's mean-of-rank-gradients.
+
+        Returns {"loss": device scalar, "tally": LossTally}; nothing synchronises the host."""
+        imgs, lbls = batch if isinstance(batch, (list, tuple)) else (batch["image"], batch["label"])
+        imgs = _pick_first_if_seq(imgs)
+        lbls = _pick_first_if_seq(lbls)
+        core: UNet3D_SpectralCore = self.model
+        if imgs.ndim == 4:
+            imgs = imgs.unsqueeze(1)
+        core.materialize(imgs.shape[2])
+        dev = core._flat.device
+        imgs = imgs.to(dev, non_blocking=True)
+        lbls = lbls.to(dev, non_blocking=True)
+        if lbls.dtype not in (torch.uint8, torch.int64):
+            lbls = lbls.long()
+        st = self._fused
+        if st is None or st["flat"] is not core._flat:
+            st = self._fused = dict(flat=core._flat, grad=torch.zeros_like(core._flat), m=torch.zeros_like(core._flat),
+                                    v=torch.zeros_like(core._flat), step=0,
+                                    tally=LossTally(self.hparams.num_classes, dev))
+            st["G"] = core._views(st["grad"])
+        st["grad"].zero_()
+        st["tally"].zero()
+        with torch.no_grad():
+            core.engine.train_step(imgs, lbls, st["G"], st["tally"], group=sample_group or core.sample_group,
+                                   ignore_index=IGNORE_INDEX)
+            world = 1
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                world = torch.distributed.get_world_size()
+                if world > 1:
+                    torch.distributed.all_reduce(st["grad"])
+            if optimize:
+                st["step"] += 1
+                n = core._n_eager
+                ops.adam_step(core._flat[:n], st["grad"][:n], st["m"][:n], st["v"][:n], float(self.hparams.lr), 0.9, 0.999,
+                              1e-8, st["step"], 1.0 / world)
+                core.engine.invalidate_weights()   # written behind torch's back: re-pack the bf16 operands
+            loss = st["tally"].loss()
+        return {"loss": loss, "tally": st["tally"]}
+
+    def fused_grads(self) -> Dict[str, torch.Tensor]:
+        """Gradient views (by core parameter name) of the last fit_step."""
+        return self._fused["G"]
+
+    def step_metrics(self, tally: LossTally, total_voxels: int):
+        """per_class_metrics_3d's 9-tuple from a fit_step tally (one device->host copy)."""
+        return metrics_from_confusion(tally.confusion.cpu().numpy(), total_voxels)
+
+
+class LitSPCT_EFiLM_FourierGate(BaseLitModel):
+    """"SPFF-UNet" (models.py:1558-1564, config.py:423-428)."""
+
+    def __init__(self, num_classes=NUM_CLASSES, lr=BEST_LR, base=32, ksd=3, use_se=True, use_specse=True,
+                 use_spatial=False, use_skip_gate=False, **kw):
+        super().__init__(num_classes=num_classes, lr=lr, is_3d=True)
+        self.model = build_spct_energyfilm_fourier(num_classes=num_classes, base=base, ksd=ksd, use_se=use_se,
+                                                   use_specse=use_specse, use_spatial=use_spatial,
+                                                   use_skip_gate=use_skip_gate, **kw)
+
+
+class LitSPCT_EnergyFiLM(BaseLitModel):
+    """"E_SP_UNet": EnergyFiLM only (models.py:1565-1573)."""
+
+    def __init__(self, num_classes=NUM_CLASSES, lr=BEST_LR, base=32, ksd=3, use_se=True, use_specse=True,
+                 use_spatial=False, use_skip_gate=False, **kw):
+        super().__init__(num_classes=num_classes, lr=lr, is_3d=True, **kw)
+        core = UNet3D_SpectralCore(in_channels=1, num_classes=num_classes, base=base, ksd=ksd, use_se=use_se,
+                                   use_specse=use_specse, use_spatial=use_spatial, use_skip_gate=use_skip_gate)
+        self.model = upgrade_spct_with_novel_blocks(core, use_efilm=True, use_fouriergate=False, use_moe=False)
+
+
+class LitSPCT_FourierGate(BaseLitModel):
+    """"FG_SP_UNet": FourierGate only (models.py:1575-1583)."""
+
+    def __init__(self, num_classes=NUM_CLASSES, lr=BEST_LR, base=32, ksd=3, use_se=True, use_specse=True,
+                 use_spatial=False, use_skip_gate=False, **kw):
+        super().__init__(num_classes=num_classes, lr=lr, is_3d=True, **kw)
+        core = UNet3D_SpectralCore(in_channels=1, num_classes=num_classes, base=base, ksd=ksd, use_se=use_se,
+                                   use_specse=use_specse, use_spatial=use_spatial, use_skip_gate=use_skip_gate)
+        self.model = upgrade_spct_with_novel_blocks(core, use_efilm=False, use_fouriergate=True, use_moe=False)
+
+
+class LitSPCT_ControlUNet(BaseLitModel):
+    """"PlainCore_UNet": the same core with plain double-conv blocks and no gates (models.py:1594-1607)."""
+
+    def __init__(self, num_classes=NUM_CLASSES, lr=BEST_LR, base=32, ksd=3, use_se=False, use_specse=False,
+                 use_spatial=False, use_skip_gate=False, **kw):
+        super().__init__(num_classes=num_classes, lr=lr, is_3d=True, **kw)
+        self.model = UNet3D_SpectralCore(in_channels=1, num_classes=num_classes, base=base, ksd=ksd, use_se=use_se,
+                                         use_specse=use_specse, use_spatial=use_spatial, use_skip_gate=use_skip_gate)

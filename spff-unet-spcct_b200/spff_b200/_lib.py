@@ -97,7 +97,53 @@ def check(code: int, what: str = "") -> None:
         raise RuntimeError(f"libspff_b200 {what} failed ({code}): {msg.decode() if msg else ''}")
 
 
+# C-ABI compute calls made by this process (each enqueues one or two kernels); bench.py reports the
+# number issued inside its timed region as `gpu_launches`.
+CALLS = 0
+
+
+class Profile:
+    """Optional per-call device timing (CUDA events on the launching stream around each C-ABI call
+    whose name passes `select`). `note` carries the algorithmic work of the next call (FLOPs or
+    bytes), set by the ops wrappers. Used by bench.py for the roofline line; off by default."""
+
+    def __init__(self, select=None):
+        self.select = select
+        self.records = []   # (name, work, start_event, end_event)
+
+    def summary(self):
+        """name -> (launches, total ms, total work); synchronises."""
+        import torch
+
+        torch.cuda.synchronize()
+        out = {}
+        for name, work, e0, e1 in self.records:
+            n, ms, w = out.get(name, (0, 0.0, 0.0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1), w + (work or 0.0))
+        return out
+
+
+PROFILE = None   # set to a Profile() to time calls
+NOTE = None      # algorithmic work of the next call
+
+
 def call(name: str, *args) -> None:
+    global CALLS, NOTE
+    CALLS += 1
+    prof = PROFILE
+    if prof is not None and (prof.select is None or prof.select(name)):
+        import torch
+
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        prof.records.append((name, NOTE, e0, e1))
+        NOTE = None
+        check(rc, name)
+        return
+    NOTE = None
     check(getattr(lib, name)(*args), name)
 
 

@@ -1,0 +1,529 @@
+"""Execution engine of the depth-preserving SPCT U-Net family on the B200 kernels.
+
+This is the host-side schedule behind `innovative3D.models.UNet3D_SpectralCore.forward` of this tree:
+it turns one forward (+ loss + backward) of the reference graph
+
+    UNet3D_SpectralCore.forward                      reference innovative3D/models.py:693-701
+      _DoubleConvSpectral(_Novel).forward            models.py:620-625, 1473-1478
+      _post = SpectralSE -> ChannelSE                models.py:684-685
+      MaxPool3d((1,2,2)) / ConvTranspose3d / cat     models.py:658-672, 687-691
+      out = Conv3d(32, K, 1)                         models.py:674
+    ce_plus_macro_dice_loss                          helpers.py:797-803
+
+into launches of the C ABI (include/spff_b200.h). Everything here is enqueue-only: no host
+synchronisation, no `.item()`. There is no PyTorch fallback for any of the compute.
+
+Data layout in HBM. Activations are bf16, position-major [n, d, h, w, C] (channels innermost). The
+three skip concatenations never happen as copies: a level owns ONE buffer `cat[l]` of 2*C_l
+channels, the transposed conv writes channels [0, C_l) ("up first", models.py:691) and the encoder
+block of that level writes its output into channels [C_l, 2*C_l) — the decoder conv reads the buffer
+as a plain 2*C_l-channel tensor. Gradients mirror that (`dcat[l]`).
+
+Samples are independent through the whole graph (InstanceNorm and every gate are per sample), so a
+batch is processed in sample groups ("micro-batches") whose buffers are reused; weight gradients
+accumulate (beta = 1) into one flat fp32 buffer, the CE normaliser N_valid is counted over the whole
+batch first. This is exact, not an approximation.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops, tables
+from ._lib import Shape
+
+GATE_EFILM, GATE_FOURIER, GATE_SPECSE, GATE_CHANSE = 1, 2, 4, 8
+BLOCKS = ("enc1", "enc2", "enc3", "bott", "dec3", "dec2", "dec1")
+_LEVEL = {"enc1": 1, "enc2": 2, "enc3": 3, "bott": 4, "dec3": 3, "dec2": 2, "dec1": 1}
+_STAGE = {"enc1": 0, "enc2": 1, "enc3": 2, "bott": 3}
+SLOPE = 0.01      # nn.LeakyReLU(1e-2)            models.py:175-181
+EPS = 1e-5        # nn.InstanceNorm3d(eps=1e-5)   models.py:170
+
+
+@dataclass(frozen=True)
+class NetConfig:
+    """Static structure of one variant (what `config.VARIANTS` builders pass to the core)."""
+    num_classes: int = 13
+    base: int = 32
+    conv_names: Tuple[str, str] = ("pre", "body")   # ("b1", "b2") for the plain _DoubleConvSpectral
+    efilm: bool = True
+    fgate: bool = True
+    specse: bool = True
+    chanse: bool = True
+
+    def block_flags(self, block: str) -> int:
+        f = (GATE_EFILM if self.efilm else 0) | (GATE_FOURIER if self.fgate else 0)
+        if block in _STAGE:  # `_post` runs on encoder / bottleneck outputs only (models.py:694-697)
+            f |= (GATE_SPECSE if self.specse else 0) | (GATE_CHANSE if self.chanse else 0)
+        return f
+
+    def channels(self, block: str) -> Tuple[int, int]:
+        f = self.base
+        return {"enc1": (1, f), "enc2": (f, 2 * f), "enc3": (2 * f, 4 * f), "bott": (4 * f, 8 * f),
+                "dec3": (8 * f, 4 * f), "dec2": (4 * f, 2 * f), "dec1": (2 * f, f)}[block]
+
+
+class _Pool:
+    """Bump allocator over one zero-able device buffer (statistics and reduction targets that the
+    kernels accumulate into: one memset per pass instead of one per tensor)."""
+
+    def __init__(self, dtype, device):
+        self.dtype, self.device = dtype, device
+        self.items: List[Tuple[Tuple[int, ...], int]] = []
+        self.total = 0
+        self.buf: Optional[torch.Tensor] = None
+
+    def reserve(self, *shape) -> int:
+        n = 1
+        for s in shape:
+            n *= s
+        n = (n + 3) // 4 * 4   # keep 16-byte alignment for fp32 / 32 for fp64
+        self.items.append((tuple(shape), self.total))
+        self.total += n
+        return len(self.items) - 1
+
+    def commit(self):
+        self.buf = torch.zeros(max(self.total, 4), dtype=self.dtype, device=self.device)
+
+    def get(self, idx: int) -> torch.Tensor:
+        shape, off = self.items[idx]
+        n = 1
+        for s in shape:
+            n *= s
+        return self.buf[off:off + n].view(shape)
+
+    def zero(self):
+        self.buf.zero_()
+
+
+class _GroupBuffers:
+    """Every activation, statistic and scratch gradient of one sample group of fixed shape."""
+
+    def __init__(self, cfg: NetConfig, n: int, d: int, h: int, w: int, device, train: bool):
+        if h % 8 or w % 8:
+            raise ValueError(f"H, W must be multiples of 8 for the SPCT family (got {h} x {w}); the reference's "
+                             "trilinear fallback for odd sizes (models.py:689-690) is not on this path")
+        self.n, self.d, self.h, self.w, self.train = n, d, h, w, train
+        f = cfg.base
+        if os.getenv("SPFF_POISON", "0") == "1":   # test hook: every activation starts as NaN
+            bf = lambda hh, ww, c: torch.full((n, d, hh, ww, c), float("nan"), dtype=torch.bfloat16, device=device)
+        else:
+            bf = lambda hh, ww, c: torch.empty(n, d, hh, ww, c, dtype=torch.bfloat16, device=device)
+        self.C = {l: f * 2 ** (l - 1) for l in (1, 2, 3, 4)}
+        self.HW = {l: (h >> (l - 1), w >> (l - 1)) for l in (1, 2, 3, 4)}
+        self.cat = {l: bf(*self.HW[l], 2 * self.C[l]) for l in (1, 2, 3)}
+        self.pool = {l: bf(*self.HW[l + 1], self.C[l]) for l in (1, 2, 3)}    # pooled output of level l
+        self.x1, self.a1, self.x2, self.out = {}, {}, {}, {}
+        self.f64 = _Pool(torch.float64, device)
+        self.f32 = _Pool(torch.float32, device)
+        self.idx: Dict[str, int] = {}
+        for b in BLOCKS:
+            l = _LEVEL[b]
+            c = self.C[l]
+            hh, ww = self.HW[l]
+            self.x1[b] = bf(hh, ww, c)
+            self.a1[b] = bf(hh, ww, c)
+            self.x2[b] = bf(hh, ww, c)
+            self.out[b] = self.cat[l][..., c:] if b.startswith("enc") else bf(hh, ww, c)
+            for j in (1, 2):
+                self.idx[f"{b}.stats{j}"] = self.f64.reserve(n, c, 2)
+            self.idx[f"{b}.S"] = self.f32.reserve(n, d, c)
+        self.f64.commit()
+        self.f32.commit()
+        self.coef = {f"{b}.{j}": torch.empty(n, self.C[_LEVEL[b]], 4, device=device) for b in BLOCKS for j in (1, 2)}
+        self.P = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
+        self.Q = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
+        self.logits = torch.empty(n, cfg.num_classes, d, h, w, device=device)
+        self.x_in: Optional[torch.Tensor] = None   # fp32 [n,1,d,h,w] network input of this group
+        if train:
+            self.dcat = {l: bf(*self.HW[l], 2 * self.C[l]) for l in (1, 2, 3)}
+            self.gout = {l: bf(*self.HW[l], self.C[l]) for l in (1, 2, 3, 4)}
+            self.t1 = {l: bf(*self.HW[l], self.C[l]) for l in (1, 2, 3, 4)}
+            self.t2 = {l: bf(*self.HW[l], self.C[l]) for l in (1, 2, 3, 4)}
+            self.dpool = {l: bf(*self.HW[l + 1], self.C[l]) for l in (1, 2, 3)}
+            self.b32 = _Pool(torch.float32, device)
+            self.b64 = _Pool(torch.float64, device)
+            for b in BLOCKS:
+                c = self.C[_LEVEL[b]]
+                for j in (1, 2):
+                    self.idx[f"{b}.R{j}"] = self.b32.reserve(n, d, c, 6)
+            for up, c in (("up3", self.C[3]), ("up2", self.C[2]), ("up1", self.C[1])):
+                self.idx[f"{up}.bstats"] = self.b64.reserve(n, c, 2)
+            self.b32.commit()
+            self.b64.commit()
+            self.bcoef = {f"{b}.{j}": torch.empty(n, self.C[_LEVEL[b]], 4, device=device) for b in BLOCKS for j in (1, 2)}
+            self.dSa = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
+            self.Pout = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
+
+    def dlogits(self) -> torch.Tensor:
+        if getattr(self, "_dlogits", None) is None:
+            self._dlogits = torch.empty_like(self.logits)
+        return self._dlogits
+
+    def shape(self, level: int) -> Shape:
+        hh, ww = self.HW[level]
+        return Shape(self.n, self.d, hh, ww)
+
+
+class GateTables:
+    """Per-step parameter-only tensors of the gates (tables.py) plus their gradient accumulators.
+
+    The tables are built from detached leaf copies of the EFiLM MLP / FourierGate parameters, so
+    that `finish()` can push the accumulated table gradients through the few torch ops of tables.py
+    without touching the caller's autograd graph."""
+
+    _TABLE_PARAMS = ("efilm.mlp.0.weight", "efilm.mlp.0.bias", "efilm.mlp.2.weight", "efilm.mlp.2.bias",
+                     "fgate.freq_mask", "fgate.mag_scale")
+
+    def __init__(self, cfg: NetConfig, params: Dict[str, torch.Tensor], frames: int, need_grad: bool):
+        self.g1: Dict[str, Optional[torch.Tensor]] = {}
+        self.bt: Dict[str, Optional[torch.Tensor]] = {}
+        self.kfg: Dict[str, Optional[torch.Tensor]] = {}
+        self.se: Dict[str, Optional[tuple]] = {}
+        self.dg1: Dict[str, Optional[torch.Tensor]] = {}
+        self.dbt: Dict[str, Optional[torch.Tensor]] = {}
+        self.dkfg: Dict[str, Optional[torch.Tensor]] = {}
+        self.leaves: Dict[str, torch.Tensor] = {}
+        self._live: List[torch.Tensor] = []     # tables with a graph, paired with self._grads
+        self._grads: List[torch.Tensor] = []
+
+        def leaf(name):
+            t = params[name].detach()
+            if need_grad:
+                t = t.clone().requires_grad_(True)
+                self.leaves[name] = t
+            return t
+
+        with torch.set_grad_enabled(need_grad):
+            for b in BLOCKS:
+                c = cfg.channels(b)[1]
+                self.g1[b] = self.bt[b] = self.kfg[b] = self.se[b] = None
+                self.dg1[b] = self.dbt[b] = self.dkfg[b] = None
+                if cfg.efilm:
+                    g1, bt = tables.efilm_tables(leaf(f"{b}.efilm.mlp.0.weight"), leaf(f"{b}.efilm.mlp.0.bias"),
+                                                 leaf(f"{b}.efilm.mlp.2.weight"), leaf(f"{b}.efilm.mlp.2.bias"), c, frames)
+                    self.g1[b], self.bt[b] = g1, bt
+                    if need_grad:
+                        self.dg1[b], self.dbt[b] = torch.zeros_like(g1), torch.zeros_like(bt)
+                        self._live += [g1, bt]
+                        self._grads += [self.dg1[b], self.dbt[b]]
+                if cfg.fgate:
+                    k = tables.fourier_kernel(leaf(f"{b}.fgate.freq_mask"), leaf(f"{b}.fgate.mag_scale"), frames)
+                    self.kfg[b] = k
+                    if need_grad:
+                        self.dkfg[b] = torch.zeros_like(k)
+                        self._live.append(k)
+                        self._grads.append(self.dkfg[b])
+                if cfg.chanse and b in _STAGE:
+                    i = _STAGE[b]
+                    w1 = params[f"se.{i}.fc.0.weight"].detach()
+                    w2 = params[f"se.{i}.fc.2.weight"].detach()
+                    self.se[b] = (w1.reshape(w1.shape[0], w1.shape[1]), params[f"se.{i}.fc.0.bias"].detach(),
+                                  w2.reshape(w2.shape[0], w2.shape[1]), params[f"se.{i}.fc.2.bias"].detach())
+
+    @staticmethod
+    def _d(t):
+        return t.detach() if t is not None else None
+
+    def finish(self, G: Dict[str, torch.Tensor]):
+        """G[name] += gradient of the EFiLM MLP / FourierGate parameters from the accumulated table
+        gradients (dg1, dbt, dkfg)."""
+        if not self._live:
+            return
+        torch.autograd.backward(self._live, self._grads)
+        for name, t in self.leaves.items():
+            if t.grad is not None:
+                G[name].add_(t.grad.view_as(G[name]))
+
+
+class SpffEngine:
+    """Forward / backward schedule of one SPCT-family network over the C ABI.
+
+    `params` maps the core module's parameter names (no `model.` prefix: `enc1.pre.0.weight`, …,
+    the key surface of SURVEY.md §8b) to CUDA fp32 tensors. The engine never owns parameters; the
+    packed bf16 GEMM operands it derives from them are refreshed by `refresh_weights()`.
+    """
+
+    def __init__(self, cfg: NetConfig, params: Callable[[], Dict[str, torch.Tensor]],
+                 versions: Optional[Callable[[], tuple]] = None):
+        self.cfg = cfg
+        self._params = params
+        self._versions = versions    # changes whenever a parameter was written through torch
+        self._packed: Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]] = {}
+        self._packed_key = None
+        self._bufs: Dict[tuple, _GroupBuffers] = {}
+
+    # ------------------------------------------------------------------------------------------
+    def params(self) -> Dict[str, torch.Tensor]:
+        return self._params()
+
+    def refresh_weights(self, force: bool = False):
+        """Re-pack conv / transposed-conv weights into the bf16 operand layouts when any changed."""
+        p = self.params()
+        names = [f"{b}.{cn}.0.weight" for b in BLOCKS for cn in self.cfg.conv_names] + ["up3.weight", "up2.weight", "up1.weight"]
+        key = (tuple(p[n].data_ptr() for n in names), self._versions() if self._versions else None)
+        if self._versions is None:
+            force = True
+        if not force and key == self._packed_key:
+            return
+        for b in BLOCKS:
+            for j, cn in enumerate(self.cfg.conv_names):
+                if b == "enc1" and j == 0:
+                    continue   # the Cin = 1 stem reads the fp32 weight directly
+                self._packed[f"{b}.{j + 1}"] = ops.pack_conv3_weight(p[f"{b}.{cn}.0.weight"])
+        for up in ("up3", "up2", "up1"):
+            self._packed[up] = ops.pack_convt_weight(p[f"{up}.weight"])
+        self._packed_key = key
+
+    def invalidate_weights(self):
+        self._packed_key = None
+
+    def buffers(self, n, d, h, w, device, train: bool, fresh: bool = False) -> _GroupBuffers:
+        if fresh:
+            return _GroupBuffers(self.cfg, n, d, h, w, device, train)
+        key = (n, d, h, w, str(device), train)
+        b = self._bufs.get(key)
+        if b is None:
+            b = self._bufs[key] = _GroupBuffers(self.cfg, n, d, h, w, device, train)
+        return b
+
+    def release_buffers(self):
+        self._bufs.clear()
+
+    # ------------------------------------------------------------------------------------------
+    # forward of one sample group
+    # ------------------------------------------------------------------------------------------
+    def _block_fwd(self, B: _GroupBuffers, T: GateTables, b: str, xin: Optional[torch.Tensor], pool_to):
+        cfg, p = self.cfg, self.params()
+        l = _LEVEL[b]
+        cin, c = cfg.channels(b)
+        cn1, cn2 = cfg.conv_names
+        shp = B.shape(l)
+        count = B.d * shp.h * shp.w
+        # conv1 -> IN statistics -> a1 = lrelu(IN(x1))
+        if b == "enc1":
+            ops.conv3d_stem_fwd(B.x_in, p[f"{b}.{cn1}.0.weight"], B.x1[b], c)
+        else:
+            ops.conv3d_k3_fwd(xin, cin, self._packed[f"{b}.1"][0], B.x1[b], c)
+        st1 = B.f64.get(B.idx[f"{b}.stats1"])
+        ops.in_stats(B.x1[b], c, st1)
+        ops.in_coeffs(st1, p[f"{b}.{cn1}.1.weight"], p[f"{b}.{cn1}.1.bias"], EPS, B.n, c, count, B.coef[f"{b}.1"])
+        ops.norm_act_apply(B.x1[b], B.coef[f"{b}.1"], B.a1[b], c, SLOPE)
+        # conv2 -> IN statistics -> (S -> P,Q) -> out = lrelu(IN(x2))*P + Q (+ pooled copy)
+        ops.conv3d_k3_fwd(B.a1[b], c, self._packed[f"{b}.2"][0], B.x2[b], c)
+        st2 = B.f64.get(B.idx[f"{b}.stats2"])
+        ops.in_stats(B.x2[b], c, st2)
+        ops.in_coeffs(st2, p[f"{b}.{cn2}.1.weight"], p[f"{b}.{cn2}.1.bias"], EPS, B.n, c, count, B.coef[f"{b}.2"])
+        flags = cfg.block_flags(b)
+        P = Q = None
+        if flags:
+            S = B.f32.get(B.idx[f"{b}.S"])
+            ops.norm_act_reduce(B.x2[b], B.coef[f"{b}.2"], S, c, SLOPE)
+            P, Q = B.P[b], B.Q[b]
+            ops.gate_micro_fwd(S, T._d(T.g1[b]), T._d(T.bt[b]), T._d(T.kfg[b]), T.se[b], flags, c, shp, P, Q)
+        ops.norm_act_affine_apply(B.x2[b], B.coef[f"{b}.2"], P, Q, B.out[b], pool_to, c, SLOPE)
+
+    def forward_group(self, B: _GroupBuffers, T: GateTables, x: torch.Tensor, head: str = "logits",
+                      logits_out: Optional[torch.Tensor] = None, labels_out: Optional[torch.Tensor] = None):
+        """x: fp32 [n,1,d,h,w] contiguous. head = "logits" (fp32 [n,K,d,h,w] into logits_out, default
+        B.logits), "argmax" (uint8 label map [n,d,h,w] into labels_out) or "none"."""
+        p = self.params()
+        B.x_in = x
+        B.f64.zero()
+        B.f32.zero()
+        self._block_fwd(B, T, "enc1", None, B.pool[1])
+        self._block_fwd(B, T, "enc2", B.pool[1], B.pool[2])
+        self._block_fwd(B, T, "enc3", B.pool[2], B.pool[3])
+        self._block_fwd(B, T, "bott", B.pool[3], None)
+        prev = B.out["bott"]
+        for l, up, dec in ((3, "up3", "dec3"), (2, "up2", "dec2"), (1, "up1", "dec1")):
+            cu = B.C[l]
+            ops.convt_k122_fwd(prev, 2 * cu, self._packed[up][0], p[f"{up}.bias"], B.cat[l][..., :cu], cu)
+            self._block_fwd(B, T, dec, B.cat[l], None)
+            prev = B.out[dec]
+        if head == "logits":
+            ops.head_fwd(prev, p["out.weight"], p["out.bias"], B.logits if logits_out is None else logits_out)
+        elif head == "argmax":
+            ops.head_argmax(prev, p["out.weight"], p["out.bias"], labels_out)
+
+    # ------------------------------------------------------------------------------------------
+    # backward of one sample group
+    # ------------------------------------------------------------------------------------------
+    def _block_bwd(self, B: _GroupBuffers, T: GateTables, G: Dict[str, torch.Tensor], b: str, dout: torch.Tensor,
+                   xin: Optional[torch.Tensor], dxin: Optional[torch.Tensor]):
+        cfg, p = self.cfg, self.params()
+        l = _LEVEL[b]
+        cin, c = cfg.channels(b)
+        cn1, cn2 = cfg.conv_names
+        shp = B.shape(l)
+        flags = cfg.block_flags(b)
+        t1, t2 = B.t1[l], B.t2[l]
+        # tail + IN2 + lrelu backward
+        R2 = B.b32.get(B.idx[f"{b}.R2"])
+        ops.norm_act_bwd_reduce(dout, B.x2[b], B.coef[f"{b}.2"], R2, c, SLOPE)
+        S = B.f32.get(B.idx[f"{b}.S"]) if flags else None
+        dse = None
+        if flags & GATE_CHANSE:
+            i = _STAGE[b]
+            dse = (G[f"se.{i}.fc.0.weight"].view(-1, c), G[f"se.{i}.fc.0.bias"], G[f"se.{i}.fc.2.weight"].view(c, -1),
+                   G[f"se.{i}.fc.2.bias"])
+        ops.gate_micro_bwd(R2, S, B.coef[f"{b}.2"], p[f"{b}.{cn2}.1.weight"], T._d(T.g1[b]), T._d(T.bt[b]), T._d(T.kfg[b]),
+                           T.se[b], flags, c, shp, B.bcoef[f"{b}.2"], B.dSa[b] if flags else None,
+                           B.Pout[b] if flags else None, G[f"{b}.{cn2}.1.weight"], G[f"{b}.{cn2}.1.bias"],
+                           T.dg1[b], T.dbt[b], T.dkfg[b], dse)
+        ops.norm_act_bwd_apply(dout, B.x2[b], B.coef[f"{b}.2"], B.bcoef[f"{b}.2"], B.Pout[b] if flags else None,
+                               B.dSa[b] if flags else None, t1, c, SLOPE)
+        # conv2 backward
+        ops.conv3d_k3_wgrad(B.a1[b], c, t1, c, G[f"{b}.{cn2}.0.weight"], 1.0)
+        ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.2"][1], t2, c)
+        # IN1 + lrelu backward
+        R1 = B.b32.get(B.idx[f"{b}.R1"])
+        ops.norm_act_bwd_reduce(t2, B.x1[b], B.coef[f"{b}.1"], R1, c, SLOPE)
+        ops.gate_micro_bwd(R1, None, B.coef[f"{b}.1"], p[f"{b}.{cn1}.1.weight"], None, None, None, None, 0, c, shp,
+                           B.bcoef[f"{b}.1"], None, None, G[f"{b}.{cn1}.1.weight"], G[f"{b}.{cn1}.1.bias"], None, None,
+                           None, None)
+        ops.norm_act_bwd_apply(t2, B.x1[b], B.coef[f"{b}.1"], B.bcoef[f"{b}.1"], None, None, t1, c, SLOPE)
+        # conv1 backward
+        if b == "enc1":
+            ops.conv3d_stem_wgrad(B.x_in, t1, c, G[f"{b}.{cn1}.0.weight"], 1.0)
+        else:
+            ops.conv3d_k3_wgrad(xin, cin, t1, c, G[f"{b}.{cn1}.0.weight"], 1.0)
+            ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.1"][1], dxin, cin)
+
+    def backward_group(self, B: _GroupBuffers, T: GateTables, G: Dict[str, torch.Tensor], dlogits: torch.Tensor):
+        """Accumulates (+=) every parameter gradient of this group into the fp32 tensors of `G`
+        (shaped like the parameters). dlogits: fp32 [n,K,d,h,w]."""
+        p = self.params()
+        B.b32.zero()
+        B.b64.zero()
+        ops.head_bwd(dlogits, B.out["dec1"], p["out.weight"], B.gout[1], G["out.weight"].view(-1, self.cfg.base),
+                     G["out.bias"], 1.0)
+        for l, up, dec, below in ((1, "up1", "dec1", "dec2"), (2, "up2", "dec2", "dec3"), (3, "up3", "dec3", "bott")):
+            cu = B.C[l]
+            self._block_bwd(B, T, G, dec, B.gout[l], B.cat[l], B.dcat[l])
+            dy = B.dcat[l][..., :cu]
+            xb = B.out[below]
+            ops.convt_k122_wgrad(xb, 2 * cu, dy, cu, G[f"{up}.weight"], 1.0)
+            ops.in_stats(dy, cu, B.b64.get(B.idx[f"{up}.bstats"]))
+            ops.convt_k122_dgrad(dy, cu, self._packed[up][1], B.gout[l + 1], 2 * cu)
+        self._block_bwd(B, T, G, "bott", B.gout[4], B.pool[3], B.dpool[3])
+        for l, enc in ((3, "enc3"), (2, "enc2"), (1, "enc1")):
+            c = B.C[l]
+            dskip = B.dcat[l][..., c:]
+            ops.maxpool_bwd_add(B.dpool[l], B.out[enc], dskip, c, True)
+            if l > 1:
+                self._block_bwd(B, T, G, enc, dskip, B.pool[l - 1], B.dpool[l - 1])
+            else:
+                self._block_bwd(B, T, G, enc, dskip, None, None)
+        # ConvTranspose3d bias gradient = column sums of dy (fp64 per-sample partials -> fp32 accumulate)
+        for up in ("up3", "up2", "up1"):
+            G[f"{up}.bias"].add_(B.b64.get(B.idx[f"{up}.bstats"])[:, :, 0].sum(0).float())
+
+    # ------------------------------------------------------------------------------------------
+    # batch-level drivers
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _check_input(x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 5 or x.shape[1] != 1:
+            raise ValueError(f"expected images [B,1,F,H,W] (energy bins on the depth axis), got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("spff_b200 runs on a B200 (sm_100) device only; the input is on the CPU and there is "
+                               "no CPU fallback")
+        return x.float().contiguous()
+
+    @staticmethod
+    def _groups(batch: int, group: int):
+        group = max(1, min(group, batch))
+        return [(i, min(batch, i + group)) for i in range(0, batch, group)]
+
+    def infer(self, x: torch.Tensor, group: int = 32, argmax: bool = False) -> torch.Tensor:
+        """Forward only. Returns fp32 logits [B,K,F,H,W], or the uint8 label map [B,F,H,W] (argmax=True,
+        first maximum wins as torch.argmax)."""
+        x = self._check_input(x)
+        bsz, _, d, h, w = x.shape
+        self.refresh_weights()
+        T = GateTables(self.cfg, self.params(), d, need_grad=False)
+        if argmax:
+            out = torch.empty(bsz, d, h, w, dtype=torch.uint8, device=x.device)
+        else:
+            out = torch.empty(bsz, self.cfg.num_classes, d, h, w, device=x.device)
+        for lo, hi in self._groups(bsz, group):
+            B = self.buffers(hi - lo, d, h, w, x.device, train=False)
+            if argmax:
+                self.forward_group(B, T, x[lo:hi], head="argmax", labels_out=out[lo:hi])
+            else:
+                self.forward_group(B, T, x[lo:hi], head="logits", logits_out=out[lo:hi])
+        return out
+
+    def forward_saved(self, x: torch.Tensor, group: int = 32):
+        """Forward that keeps every group's activations for a later `backward_saved` (the autograd
+        path behind `model(x)`; memory grows with the batch, unlike `train_step`)."""
+        x = self._check_input(x)
+        bsz, _, d, h, w = x.shape
+        self.refresh_weights()
+        T = GateTables(self.cfg, self.params(), d, need_grad=True)
+        logits = torch.empty(bsz, self.cfg.num_classes, d, h, w, device=x.device)
+        saved = []
+        for lo, hi in self._groups(bsz, group):
+            B = self.buffers(hi - lo, d, h, w, x.device, train=True, fresh=True)
+            self.forward_group(B, T, x[lo:hi], head="logits", logits_out=logits[lo:hi])
+            saved.append((lo, hi, B))
+        return logits, (T, saved)
+
+    def backward_saved(self, state, dlogits: torch.Tensor, G: Dict[str, torch.Tensor]):
+        T, saved = state
+        dlogits = dlogits.float().contiguous()
+        for lo, hi, B in saved:
+            self.backward_group(B, T, G, dlogits[lo:hi])
+        T.finish(G)
+
+    def train_step(self, x: torch.Tensor, labels: torch.Tensor, G: Dict[str, torch.Tensor], tally: "LossTally",
+                   group: int = 32, ignore_index: int = 255):
+        """Fused forward + CE/confusion + backward over the batch in sample groups. Accumulates the
+        parameter gradients of the batch-mean CE (helpers.py:798-801; the Dice term of the loss has
+        no gradient, helpers.py:782-795) into G and the loss statistics into `tally`."""
+        x = self._check_input(x)
+        bsz, _, d, h, w = x.shape
+        if labels.shape != (bsz, d, h, w):
+            raise ValueError(f"labels must be [B,F,H,W] = {(bsz, d, h, w)}, got {tuple(labels.shape)}")
+        labels = labels.contiguous()
+        self.refresh_weights()
+        T = GateTables(self.cfg, self.params(), d, need_grad=True)
+        n_valid = (labels != ignore_index).sum().reshape(1)     # the CE normaliser spans the whole batch
+        for lo, hi in self._groups(bsz, group):
+            B = self.buffers(hi - lo, d, h, w, x.device, train=True)
+            self.forward_group(B, T, x[lo:hi], head="logits")
+            ops.ce_confusion(B.logits, labels[lo:hi], ignore_index, tally.nll, tally.count, tally.confusion)
+            dlogits = B.dlogits()
+            ops.ce_grad(B.logits, labels[lo:hi], ignore_index, n_valid, None, dlogits)
+            self.backward_group(B, T, G, dlogits)
+        T.finish(G)
+
+
+class LossTally:
+    """Device-side sufficient statistics of ce_plus_macro_dice_loss and per_class_metrics_3d
+    (helpers.py:668-725, 782-803): sum of nll, number of valid voxels, [label][argmax] tally."""
+
+    def __init__(self, num_classes: int, device):
+        self.k = num_classes
+        self.nll = torch.zeros(1, dtype=torch.float64, device=device)
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+        self.confusion = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=device)
+
+    def zero(self):
+        self.nll.zero_()
+        self.count.zero_()
+        self.confusion.zero_()
+
+    def loss(self, smooth: float = 1e-6) -> torch.Tensor:
+        """CE + 0.5 * (1 - hard macro Dice over classes 1..K-1) as a device scalar (no host sync)."""
+        cm = self.confusion.double()
+        tp = cm.diagonal()[1:]
+        fp = cm.sum(0)[1:] - tp
+        fn = cm.sum(1)[1:] - tp
+        dice = ((2 * tp + smooth) / (2 * tp + fp + fn + smooth)).mean() if self.k > 1 else cm.new_ones(())
+        ce = self.nll[0] / self.count[0].clamp(min=1).double()
+        return (ce + 0.5 * (1.0 - dice)).float()

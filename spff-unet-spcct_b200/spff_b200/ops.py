@@ -26,6 +26,11 @@ def _view(t: torch.Tensor, c: int):
     return Shape(n, d, h, w), ld
 
 
+def conv3_flops(s: Shape, cin: int, cout: int) -> float:
+    """Algorithmic FLOPs of one 3x3x3 convolution pass (fwd, dgrad or wgrad): 2 * 27 * cin * cout per position."""
+    return 2.0 * 27 * cin * cout * s.n * s.d * s.h * s.w
+
+
 def conv3_kc(k_channels: int) -> int:
     return 64 if k_channels % 64 == 0 else 32
 
@@ -44,6 +49,7 @@ def conv3d_k3_fwd(x, cin, w_fwd, y, cout):
     s, ldx = _view(x, cin)
     s2, ldy = _view(y, cout)
     assert (s.n, s.d, s.h, s.w) == (s2.n, s2.d, s2.h, s2.w)
+    _lib.NOTE = conv3_flops(s, cin, cout)
     call("spff_conv3d_k3_fwd", ptr(x), ldx, cin, ptr(w_fwd), ptr(y), ldy, cout, s, stream_ptr())
 
 
@@ -51,6 +57,7 @@ def conv3d_k3_dgrad(dy, cout, w_dgrad, dx, cin):
     s, lddy = _view(dy, cout)
     s2, lddx = _view(dx, cin)
     assert (s.n, s.d, s.h, s.w) == (s2.n, s2.d, s2.h, s2.w)
+    _lib.NOTE = conv3_flops(s, cin, cout)
     call("spff_conv3d_k3_dgrad", ptr(dy), lddy, cout, ptr(w_dgrad), ptr(dx), lddx, cin, s, stream_ptr())
 
 
@@ -80,6 +87,7 @@ def conv3d_k3_wgrad(x, cin, dy, cout, dw, beta: float = 0.0, ws: torch.Tensor | 
     assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (cout, cin, 3, 3, 3)
     if ws is None:
         ws = conv3d_k3_wgrad_workspace(cin, cout, x)
+    _lib.NOTE = conv3_flops(s, cin, cout)
     call("spff_conv3d_k3_wgrad", ptr(x), ldx, cin, ptr(dy), lddy, cout, s, ptr(dw), float(beta), ptr(ws),
          ws.numel(), stream_ptr())
 
