@@ -281,8 +281,8 @@ def run_b200(args):
         }
         if not args.no_cpu and world >= 1:
             t0 = time.perf_counter()
-            cs = 2
-            times, threads = cpu_step_time(cs, reps=3, warmup=1, budget_s=40.0)
+            cs = 8
+            times, threads = cpu_step_time(cs, reps=4, warmup=1, budget_s=25.0)
             cpu_sec = min(times)
             line["cpu_baseline"] = {
                 "value": cs * FRAMES * H * W / cpu_sec, "unit": "voxels/s", "cores": threads, "kind": "port",

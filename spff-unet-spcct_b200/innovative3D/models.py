@@ -30,7 +30,7 @@ try:  # the real Lightning when it is installed (the reference pins 2.6.1, requi
 except ImportError:  # not in this image: a minimal stand-in with the same method names
     from ._lightning import pl
 
-from spff_b200 import ops
+from spff_b200 import dp, ops
 from spff_b200.engine import LossTally, NetConfig, SpffEngine
 
 from .config import BEST_LR, IGNORE_INDEX, NUM_CLASSES, NUM_FRAMES
@@ -468,16 +468,12 @@ class BaseLitModel(pl.LightningModule):
         with torch.no_grad():
             core.engine.train_step(imgs, lbls, st["G"], st["tally"], group=sample_group or core.sample_group,
                                    ignore_index=IGNORE_INDEX)
-            world = 1
-            if torch.distributed.is_available() and torch.distributed.is_initialized():
-                world = torch.distributed.get_world_size()
-                if world > 1:
-                    torch.distributed.all_reduce(st["grad"])
+            gscale = dp.allreduce_grads(st["grad"])
             if optimize:
                 st["step"] += 1
                 n = core._n_eager
                 ops.adam_step(core._flat[:n], st["grad"][:n], st["m"][:n], st["v"][:n], float(self.hparams.lr), 0.9, 0.999,
-                              1e-8, st["step"], 1.0 / world)
+                              1e-8, st["step"], gscale)
                 core.engine.invalidate_weights()   # written behind torch's back: re-pack the bf16 operands
             loss = st["tally"].loss()
         return {"loss": loss, "tally": st["tally"]}

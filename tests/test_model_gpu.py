@@ -77,7 +77,7 @@ def test_against_reference_fixture(path):
         refs = torch.from_numpy(z["g|" + name]).double()
         num += float((g[::step][:512] - refs).pow(2).sum()) * step
         den += float(refs.pow(2).sum()) * step
-        if gn > 1e-3:
+        if gn > 0.05 * float(z["grad_norms"].max()):
             assert abs(float(g.norm()) - gn) < 0.4 * gn, (name, float(g.norm()), gn)
     print(os.path.basename(path), 'logits rel', rel(logits, ref), 'whole-gradient rel', (num / den) ** 0.5)
     assert (num / den) ** 0.5 < 0.3, (num / den) ** 0.5
@@ -110,19 +110,20 @@ def _train(lit, steps, b, h, w, lr):
     return [float(l) for l in losses]
 
 
-def test_trained_weights_meet_north_star_tolerances():
+@pytest.mark.parametrize("variant", ["SPFF-UNet", "PlainCore_UNet"])
+def test_trained_weights_meet_north_star_tolerances(variant):
     """Train briefly with the fused step (loss must fall), then compare with the oracle on the trained
     weights: per-block activations <= 2e-2 rel-L2, argmax agreement >= 99.9 %, macro Dice within 1e-3,
     parameter gradients <= 2e-2 rel-L2 (conv / norm / head) on a fresh batch."""
     from innovative3D import helpers as H
     from oracle import spff_oracle as O
     torch.manual_seed(42)
-    lit = build("SPFF-UNet")
+    lit = build(variant)
     losses = _train(lit, 80, 8, 32, 32, 1e-3)
     assert losses[-1] < 0.6 * losses[0], losses[::10]
     sd = {k: v.detach().cpu().clone() for k, v in lit.state_dict().items() if not k.endswith("fgate._mask")}
     x, lab = O.phantom_batch(2, 128, 128, seed=999, ignore_frac=0.01)
-    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd, x, lab, "SPFF-UNet")
+    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd, x, lab, variant)
     xg, lg = x.cuda(), lab.cuda()
     logits = lit(xg)
     assert rel(logits, ref_logits) < 2e-2
