@@ -132,9 +132,10 @@ int spff_gate_micro_fwd(const float* S, const float* g1, const float* bt, const 
                         const float* se_b1, const float* se_w2, const float* se_b2, int hid, int flags, int c,
                         spff_shape s, float* P, float* Q, void* stream);
 /* Backward pass 1: R[n][d][c][6] += per-plane sums over (h,w) of
- *   {dout*a, dout, dout*m, m, dout*m*xhat, m*xhat},  m = lrelu'(z), z = x*A+B, a = lrelu(z). */
+ *   {dout*a, dout, dout*m, m, dout*m*xhat, m*xhat},  m = lrelu'(z), z = x*A+B, a = lrelu(z).
+ * plain != 0: only slots 2 and 4 are produced (all that spff_gate_micro_bwd(flags = 0) reads). */
 int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
-                             float* R, int c, spff_shape s, float slope, void* stream);
+                             float* R, int c, spff_shape s, float slope, int plain, void* stream);
 /* Backward micro-kernel: consumes R (and S), recomputes the gates, produces
  *   bcoef[n][c] = {gamma*rstd, mean(dz), mean(dz*xhat), 0}, dSa[n][d][c], Pout[n][d][c]
  * and ACCUMULATES (+=) dgamma[c], dbeta[c], dg1[c][d], dbt[c][d], dkfg[d], dse_*. flags == 0 is the
@@ -175,6 +176,17 @@ int spff_ce_confusion(const float* logits, const void* labels, int label_bytes, 
  * (gscale may be NULL = 1). */
 int spff_ce_grad(const float* logits, const void* labels, int label_bytes, int ignore_index, int k, spff_shape s,
                  const long long* n_valid, const float* gscale, float* dlogits, void* stream);
+
+/* Fused TRAINING head: head_fwd + ce_confusion + ce_grad + head_bwd in one pass over x; the logits
+ * are never materialised. acc/counts/confusion accumulate as in spff_ce_confusion; dx (bf16, may be
+ * NULL), dw[K][32], db[K] (= beta*old + gradient) as in spff_head_bwd with
+ * dlogits = (softmax - onehot) * gscale[0] / n_valid[0]. */
+size_t spff_head_loss_workspace(int k);
+int spff_head_loss_fused(const void* x, long long ldx, int cin, const float* w, const float* b, const void* labels,
+                         int label_bytes, int ignore_index, int k, spff_shape s, const long long* n_valid,
+                         const float* gscale, double* acc, long long* counts, long long* confusion, void* dx,
+                         long long lddx, float* dw, float* db, float beta, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ---- optimizer (models.py:591-594: torch.optim.Adam, lr 1e-4, betas (0.9,0.999), eps 1e-8) -------- */
 int spff_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,

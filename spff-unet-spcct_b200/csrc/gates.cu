@@ -353,6 +353,32 @@ gate_bwd_kernel(GateArgs a, const float* __restrict__ R, const float* __restrict
   }
 }
 
+// Gate-free case (plain InstanceNorm + LeakyReLU backward): per (n, c)
+//   bcoef = {gamma*rstd, mean(dz), mean(dz*xhat), 0},  dgamma += sum dz*xhat,  dbeta += sum dz
+// from the slots 2 and 4 of R. One thread per (sample, channel); no shared memory, no phases.
+__global__ void in_bwd_coeffs_kernel(const float* __restrict__ R, const float* __restrict__ coef,
+                                     const float* __restrict__ gamma, int n, int c, int d, float inv_dhw,
+                                     float* __restrict__ bcoef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int s = i / c, ch = i % c;
+  float sum_dz = 0.f, sum_dzx = 0.f;
+  for (int dd = 0; dd < d; ++dd) {
+    const float* r = R + ((static_cast<size_t>(s) * d + dd) * c + ch) * 6;
+    sum_dz += r[2];
+    sum_dzx += r[4];
+  }
+  const float4 cf = reinterpret_cast<const float4*>(coef)[i];
+  float4 bc;
+  bc.x = (gamma ? gamma[ch] : 1.f) * cf.w;
+  bc.y = sum_dz * inv_dhw;
+  bc.z = sum_dzx * inv_dhw;
+  bc.w = 0.f;
+  reinterpret_cast<float4*>(bcoef)[i] = bc;
+  if (dgamma) atomicAdd(dgamma + ch, sum_dzx);
+  if (dbeta) atomicAdd(dbeta + ch, sum_dz);
+}
+
 int check_gate_args(const GateArgs& a, int n) {
   if (a.c <= 0 || a.d <= 0 || a.d > kMaxD || n <= 0) {
     set_error("gate_micro: bad shape (c %d, d %d <= %d, n %d)", a.c, a.d, kMaxD, n);
@@ -410,6 +436,13 @@ int spff_gate_micro_bwd(const float* R, const float* S, const float* coef, const
   SPFF_REQUIRE(!(flags & SPFF_GATE_EFILM) || (dg1 && dbt), "gate_micro_bwd: EFILM needs dg1/dbt");
   SPFF_REQUIRE(!(flags & SPFF_GATE_FOURIER) || dkfg, "gate_micro_bwd: FOURIER needs dkfg");
   SPFF_REQUIRE(!(flags & SPFF_GATE_CHANSE) || (dse_w1 && dse_b1 && dse_w2 && dse_b2), "gate_micro_bwd: CHANSE needs d(fc)");
+  if (flags == 0 && !dSa && !Pout) {
+    const int total = s.n * c;
+    spff::in_bwd_coeffs_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        R, coef, gamma, s.n, c, s.d, 1.f / (static_cast<float>(s.d) * s.h * s.w), bcoef, dgamma, dbeta);
+    SPFF_CUDA(cudaGetLastError());
+    return 0;
+  }
   spff::GateBwdOut o{bcoef, dSa, Pout, dgamma, dbeta, dg1, dbt, dkfg, dse_w1, dse_b1, dse_w2, dse_b2};
   const size_t smem = spff::gate_smem_bytes(c, s.d);
   if (smem > 48 * 1024)

@@ -64,6 +64,38 @@ __device__ __forceinline__ void reduce_rows(float (&v)[NV], float* red, int c8, 
   __syncthreads();
 }
 
+
+// Fast path of the same reduction for c8 in {1,2,4,...,32} (every in-scope channel count): rows that
+// share a warp are folded with shuffles, the 8 warps meet in shared memory, and thread t of the
+// first L*NV threads ends up owning output element t (vector t / NV... laid out [vec][NV]) so that
+// the global atomics that follow are contiguous. `red` holds 8 * 32 * NV floats.
+// Returns true when this thread holds a valid result in `out` for output index `idx`
+// (idx = vec * NV + i); blocks with more than 256 outputs loop through `round`.
+template <int NV>
+__device__ __forceinline__ void reduce_rows_fast(float (&v)[NV], float* red, int c8) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = c8 < 32 ? c8 : 32;
+  for (int off = 16; off >= c8; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+  }
+  if (lane < L) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[(warp * L + lane) * NV + i] = v[i];
+  }
+  __syncthreads();
+}
+// sum over the 8 warps of output element idx (vec = idx / NV, i = idx % NV)
+template <int NV>
+__device__ __forceinline__ float reduce_rows_fetch(const float* red, int c8, int idx) {
+  const int L = c8 < 32 ? c8 : 32;
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < kBlock / 32; ++w) t += red[w * L * NV + idx];
+  return t;
+}
+__device__ __forceinline__ bool fast_reduce_ok(int c8) { return c8 <= 32 && (c8 & (c8 - 1)) == 0; }
+
 // ---------------------------------------------------------------------------------------------
 // InstanceNorm statistics: stats[n][c] += {sum x, sum x^2} over the block's positions (double).
 // grid = (chunks, d, n)
@@ -80,30 +112,42 @@ __global__ void __launch_bounds__(kBlock) in_stats_kernel(const __nv_bfloat16* _
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (r < g.rpi) {
-    for (int p = p0 + r; p < p1; p += g.rpi) {
-      float f[8];
-      unpack8(ldg16(x + (base + p) * ld + v * 8), f);
+    constexpr int U = 4;   // independent 16-byte loads in flight per thread
+    for (int p = p0 + r; p < p1; p += U * g.rpi) {
+      uint4 raw[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += f[i];
-        q[i] = fmaf(f[i], f[i], q[i]);
+      for (int u = 0; u < U; ++u)
+        raw[u] = (p + u * g.rpi < p1) ? ldg16(x + (base + p + u * g.rpi) * ld + v * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] = fmaf(f[i], f[i], q[i]);
+        }
       }
     }
   }
   float sq[16];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    sq[i] = s[i];
-    sq[8 + i] = q[i];
+    sq[2 * i] = s[i];          // interleaved {sum, sumsq} = the layout of stats[n][c][2]
+    sq[2 * i + 1] = q[i];
+  }
+  if (fast_reduce_ok(g.c8)) {
+    reduce_rows_fast<16>(sq, red, g.c8);
+    const int L = g.c8 < 32 ? g.c8 : 32;
+    for (int idx = threadIdx.x; idx < L * 16; idx += kBlock)
+      atomicAdd(stats + static_cast<long long>(n) * c * 2 + idx, static_cast<double>(reduce_rows_fetch<16>(red, g.c8, idx)));
+    return;
   }
   reduce_rows<16>(sq, red, g.c8, g.rpi);
   if (threadIdx.x < g.c8) {
     double* dst = stats + (static_cast<long long>(n) * c + v * 8) * 2;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(dst + 2 * i, static_cast<double>(sq[i]));
-      atomicAdd(dst + 2 * i + 1, static_cast<double>(sq[8 + i]));
-    }
+    for (int i = 0; i < 16; ++i) atomicAdd(dst + i, static_cast<double>(sq[i]));
   }
 }
 
@@ -182,20 +226,37 @@ norm_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float*
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (r < g.rpi) {
-    for (int p = p0 + r; p < p1; p += g.rpi) {
-      float f[8];
-      unpack8(ldg16(x + (base + p) * ldx + v * 8), f);
+    constexpr int U = 4;   // independent 16-byte loads in flight per thread
+    for (int p = p0 + r; p < p1; p += U * g.rpi) {
+      uint4 raw[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float z = fmaf(f[i], A[i], B[i]);
-        float a = z > 0.f ? z : z * slope;
-        if (REDUCE) acc[i] += a;
-        f[i] = AFFINE ? fmaf(a, Pv[i], Qv[i]) : a;
+      for (int u = 0; u < U; ++u)
+        if (p + u * g.rpi < p1) raw[u] = ldg16(x + (base + p + u * g.rpi) * ldx + v * 8);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (p + u * g.rpi < p1) {
+          float f[8];
+          unpack8(raw[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float z = fmaf(f[i], A[i], B[i]);
+            float a = z > 0.f ? z : z * slope;
+            if (REDUCE) acc[i] += a;
+            f[i] = AFFINE ? fmaf(a, Pv[i], Qv[i]) : a;
+          }
+          if (WRITE) stg16(y + (base + p + u * g.rpi) * ldy + v * 8, pack8(f));
+        }
       }
-      if (WRITE) stg16(y + (base + p) * ldy + v * 8, pack8(f));
     }
   }
   if (REDUCE) {
+    if (fast_reduce_ok(g.c8)) {
+      reduce_rows_fast<8>(acc, red, g.c8);
+      const int L = g.c8 < 32 ? g.c8 : 32;
+      if (threadIdx.x < L * 8)
+        atomicAdd(S + (static_cast<long long>(n) * d + dd) * c + threadIdx.x, reduce_rows_fetch<8>(red, g.c8, threadIdx.x));
+      return;
+    }
     reduce_rows<8>(acc, red, g.c8, g.rpi);
     if (threadIdx.x < g.c8) {
       float* dst = S + (static_cast<long long>(n) * d + dd) * c + v * 8;
@@ -257,11 +318,15 @@ norm_act_pool_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const f
 //   {dout*a, dout, dout*m, m, dout*m*xhat, m*xhat},  z = x*A+B, m = lrelu'(z), a = lrelu(z),
 //   xhat = (x-mean)*rstd.     grid = (chunks, d, n)
 // ---------------------------------------------------------------------------------------------
+// PLAIN = true: only {dout*m, dout*m*xhat} (slots 2 and 4) are produced - all the plain
+// InstanceNorm + LeakyReLU backward (no gate tail) needs.
+template <bool PLAIN>
 __global__ void __launch_bounds__(kBlock)
 norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ x,
                            long long ldx, const float* __restrict__ coef, float* __restrict__ R, PlaneGrid g, int d,
                            int c, float slope) {
   extern __shared__ float red[];
+  constexpr int NK = PLAIN ? 2 : 6;
   const int n = blockIdx.z, dd = blockIdx.y;
   const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
   const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
@@ -276,44 +341,73 @@ norm_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, long long ldd
       A[i] = t.x; B[i] = t.y; Mn[i] = t.z; Rs[i] = t.w;
     }
   }
-  float acc[6][8];
+  float acc[NK][8];
 #pragma unroll
-  for (int k = 0; k < 6; ++k)
+  for (int k = 0; k < NK; ++k)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
   if (r < g.rpi) {
-    for (int p = p0 + r; p < p1; p += g.rpi) {
-      float f[8], go[8];
-      unpack8(ldg16(x + (base + p) * ldx + v * 8), f);
-      unpack8(ldg16(dout + (base + p) * lddo + v * 8), go);
+    constexpr int U = 2;   // 2 x (x, dout) 16-byte loads in flight per thread
+    for (int p = p0 + r; p < p1; p += U * g.rpi) {
+      uint4 rx[U], rg[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float z = fmaf(f[i], A[i], B[i]);
-        const float m = z > 0.f ? 1.f : slope;
-        const float a = z * m;
-        const float xh = (f[i] - Mn[i]) * Rs[i];
-        const float gm = go[i] * m;
-        acc[0][i] = fmaf(go[i], a, acc[0][i]);
-        acc[1][i] += go[i];
-        acc[2][i] += gm;
-        acc[3][i] += m;
-        acc[4][i] = fmaf(gm, xh, acc[4][i]);
-        acc[5][i] = fmaf(m, xh, acc[5][i]);
+      for (int u = 0; u < U; ++u) {
+        const bool ok = p + u * g.rpi < p1;
+        rx[u] = ok ? ldg16(x + (base + p + u * g.rpi) * ldx + v * 8) : make_uint4(0, 0, 0, 0);
+        rg[u] = ok ? ldg16(dout + (base + p + u * g.rpi) * lddo + v * 8) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float f[8], go[8];
+        unpack8(rx[u], f);
+        unpack8(rg[u], go);   // out-of-range rows carry dout = 0 and contribute nothing to slots 0,1,2,4
+        const float live = (p + u * g.rpi < p1) ? 1.f : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float z = fmaf(f[i], A[i], B[i]);
+          const float m = z > 0.f ? 1.f : slope;
+          const float xh = (f[i] - Mn[i]) * Rs[i];
+          const float gm = go[i] * m;
+          if (PLAIN) {
+            acc[0][i] += gm;
+            acc[1][i] = fmaf(gm, xh, acc[1][i]);
+          } else {
+            const float ml = m * live;
+            acc[0][i] = fmaf(go[i], z * m, acc[0][i]);
+            acc[1][i] += go[i];
+            acc[2][i] += gm;
+            acc[3][i] += ml;
+            acc[4][i] = fmaf(gm, xh, acc[4][i]);
+            acc[5][i] = fmaf(ml, xh, acc[5][i]);
+          }
+        }
       }
     }
   }
+  float* Rp = R + (static_cast<long long>(n) * d + dd) * c * 6;
+  const bool fast = fast_reduce_ok(g.c8);
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    reduce_rows<8>(acc[k], red, g.c8, g.rpi);
-    if (threadIdx.x < g.c8) {
-      float* dst = R + ((static_cast<long long>(n) * d + dd) * c + v * 8) * 6 + k;
+  for (int k = 0; k < NK; ++k) {
+    const int slot = PLAIN ? (k == 0 ? 2 : 4) : k;
+    if (fast) {
+      reduce_rows_fast<8>(acc[k], red, g.c8);
+      const int L = g.c8 < 32 ? g.c8 : 32;
+      if (threadIdx.x < L * 8) atomicAdd(Rp + threadIdx.x * 6 + slot, reduce_rows_fetch<8>(red, g.c8, threadIdx.x));
+      __syncthreads();
+    } else {
+      reduce_rows<8>(acc[k], red, g.c8, g.rpi);
+      if (threadIdx.x < g.c8) {
+        float* dst = Rp + v * 8 * 6 + slot;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(dst + 6 * i, acc[k][i]);
+        for (int i = 0; i < 8; ++i) atomicAdd(dst + 6 * i, acc[k][i]);
+      }
     }
   }
 }
 
 // backward pass 2: dx = c1*(dz - c2 - xhat*c3), dz = (dout*P + dSa)*m.  bcoef[n][c] = {c1,c2,c3,-}
+// Folded per channel: dx = m * (K1*dout + K1d) + K2*x + K3 with
+//   K1 = c1*P, K1d = c1*dSa, K2 = -c1*c3*rstd, K3 = c1*(c3*rstd*mean - c2),  m = lrelu'(x*A + B).
 template <bool AFFINE>
 __global__ void __launch_bounds__(kBlock)
 norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ x,
@@ -325,38 +419,54 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo
   const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
   const int p0 = blockIdx.x * g.chunk;
   const int p1 = min(g.hw, p0 + g.chunk);
-  float A[8], B[8], Mn[8], Rs[8], C1[8], C2[8], C3[8], Pv[8], Dv[8];
+  float A[8], B[8], K1[8], K1d[8], K2[8], K3[8];
   {
     const float4* cf = reinterpret_cast<const float4*>(coef) + static_cast<long long>(n) * c + v * 8;
     const float4* bf = reinterpret_cast<const float4*>(bcoef) + static_cast<long long>(n) * c + v * 8;
+    float Pv[8], Dv[8];
+    if (AFFINE) {
+      const long long pq = (static_cast<long long>(n) * d + dd) * c + v * 8;
+      load8(P + pq, Pv);
+      load8(dSa + pq, Dv);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 t = __ldg(cf + i);
-      A[i] = t.x; B[i] = t.y; Mn[i] = t.z; Rs[i] = t.w;
-      float4 u = __ldg(bf + i);
-      C1[i] = u.x; C2[i] = u.y; C3[i] = u.z;
+      const float4 t = __ldg(cf + i);   // {A, B, mean, rstd}
+      const float4 u = __ldg(bf + i);   // {c1, c2, c3, -}
+      A[i] = t.x;
+      B[i] = t.y;
+      K1[i] = AFFINE ? u.x * Pv[i] : u.x;
+      K1d[i] = AFFINE ? u.x * Dv[i] : 0.f;
+      K2[i] = -u.x * u.z * t.w;
+      K3[i] = u.x * (u.z * t.w * t.z - u.y);
     }
-  }
-  if (AFFINE) {
-    const long long pq = (static_cast<long long>(n) * d + dd) * c + v * 8;
-    load8(P + pq, Pv);
-    load8(dSa + pq, Dv);
   }
   if (r >= g.rpi) return;
-  for (int p = p0 + r; p < p1; p += g.rpi) {
-    float f[8], go[8];
-    unpack8(ldg16(x + (base + p) * ldx + v * 8), f);
-    unpack8(ldg16(dout + (base + p) * lddo + v * 8), go);
+  constexpr int U = 2;
+  for (int p = p0 + r; p < p1; p += U * g.rpi) {
+    uint4 rx[U], rg[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float z = fmaf(f[i], A[i], B[i]);
-      const float m = z > 0.f ? 1.f : slope;
-      const float xh = (f[i] - Mn[i]) * Rs[i];
-      const float da = AFFINE ? fmaf(go[i], Pv[i], Dv[i]) : go[i];
-      const float dz = da * m;
-      f[i] = C1[i] * (dz - C2[i] - xh * C3[i]);
+    for (int u = 0; u < U; ++u) {
+      if (p + u * g.rpi < p1) {
+        rx[u] = ldg16(x + (base + p + u * g.rpi) * ldx + v * 8);
+        rg[u] = ldg16(dout + (base + p + u * g.rpi) * lddo + v * 8);
+      }
     }
-    stg16(dx + (base + p) * lddx + v * 8, pack8(f));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p + u * g.rpi < p1) {
+        float f[8], go[8];
+        unpack8(rx[u], f);
+        unpack8(rg[u], go);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float z = fmaf(f[i], A[i], B[i]);
+          const float m = z > 0.f ? 1.f : slope;
+          f[i] = fmaf(m, fmaf(K1[i], go[i], K1d[i]), fmaf(K2[i], f[i], K3[i]));
+        }
+        stg16(dx + (base + p + u * g.rpi) * lddx + v * 8, pack8(f));
+      }
+    }
   }
 }
 
@@ -538,14 +648,18 @@ int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, 
 }
 
 int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
-                             float* R, int c, spff_shape s, float slope, void* stream) {
+                             float* R, int c, spff_shape s, float slope, int plain, void* stream) {
   SPFF_ENTRY_CHECK();
   PlaneGrid g;
   dim3 grid;
   int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
   if (e) return e;
-  spff::norm_act_bwd_reduce_kernel<<<grid, kBlock, 8 * kBlock * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g, s.d, c, slope);
+  if (plain)
+    spff::norm_act_bwd_reduce_kernel<true><<<grid, kBlock, 8 * kBlock * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g, s.d, c, slope);
+  else
+    spff::norm_act_bwd_reduce_kernel<false><<<grid, kBlock, 8 * kBlock * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g, s.d, c, slope);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }

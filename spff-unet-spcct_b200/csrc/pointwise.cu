@@ -44,6 +44,36 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // stem: y[pos][co] = sum_tap x[pos+tap] * w[co][tap]     x fp32 [N,1,D,H,W], y bf16 position-major
 // one thread = one voxel x 8 output channels
 // ---------------------------------------------------------------------------------------------
+// A thread owns a strip of kStrip consecutive w positions of one (n,d,h) row and 8 (forward) or 4
+// (weight gradient) output channels: the 3 x (kStrip+2) input window of each (kd,kh) row is loaded
+// once and reused by the 3 kw taps of every position of the strip, the tap weights once per strip.
+constexpr int kStrip = 4;
+
+__device__ __forceinline__ void stem_decode(long long i, int cg, int strips, const spff_shape& s, int& v, int& w0,
+                                            int& hq, int& dq, long long& rowbase) {
+  v = static_cast<int>(i % cg);
+  const long long t = i / cg;
+  const int st = static_cast<int>(t % strips);
+  const long long row = t / strips;            // (n*d + dq)*h + hq
+  hq = static_cast<int>(row % s.h);
+  dq = static_cast<int>((row / s.h) % s.d);
+  w0 = st * kStrip;
+  rowbase = row * s.w;
+}
+
+// loads x[(dq+kd-1), (hq+kh-1), w0-1 .. w0+kStrip] (zero outside the volume)
+__device__ __forceinline__ void stem_window(const float* __restrict__ x, long long rowbase, int w0, int hq, int dq, int kd,
+                                            int kh, const spff_shape& s, float (&xw)[kStrip + 2]) {
+  const int d2 = dq + kd - 1, h2 = hq + kh - 1;
+  const bool rok = d2 >= 0 && d2 < s.d && h2 >= 0 && h2 < s.h;
+  const float* xr = x + rowbase + (static_cast<long long>(kd - 1) * s.h + (kh - 1)) * s.w + w0 - 1;
+#pragma unroll
+  for (int j = 0; j < kStrip + 2; ++j) {
+    const int w2 = w0 - 1 + j;
+    xw[j] = (rok && w2 >= 0 && w2 < s.w) ? __ldg(xr + j) : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
                 int cout, spff_shape s) {
@@ -51,48 +81,51 @@ stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_b
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) sw[(i % 27) * cout + i / 27] = w[i];
   __syncthreads();
   const int c8 = cout / 8;
-  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w * c8;
+  const int strips = (s.w + kStrip - 1) / kStrip;
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * strips * c8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % c8);
-    const long long pos = i / c8;
-    const int wq = static_cast<int>(pos % s.w);
-    const int hq = static_cast<int>((pos / s.w) % s.h);
-    const int dq = static_cast<int>((pos / (static_cast<long long>(s.w) * s.h)) % s.d);
-    float acc[8];
+    int v, w0, hq, dq;
+    long long rowbase;
+    stem_decode(i, c8, strips, s, v, w0, hq, dq, rowbase);
+    float acc[kStrip][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int j = 0; j < kStrip; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) {
-      const int d2 = dq + kd - 1;
-      if (d2 < 0 || d2 >= s.d) continue;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const int h2 = hq + kh - 1;
-        if (h2 < 0 || h2 >= s.h) continue;
+        float xw[kStrip + 2];
+        stem_window(x, rowbase, w0, hq, dq, kd, kh, s, xw);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const int w2 = wq + kw - 1;
-          if (w2 < 0 || w2 >= s.w) continue;
-          const float xv = __ldg(x + pos + (static_cast<long long>(kd - 1) * s.h + (kh - 1)) * s.w + (kw - 1));
-          const float* wr = sw + ((kd * 3 + kh) * 3 + kw) * cout + v * 8;
+          const float4* wr = reinterpret_cast<const float4*>(sw + ((kd * 3 + kh) * 3 + kw) * cout + v * 8);
+          const float4 wa = wr[0], wb = wr[1];
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(xv, wr[k], acc[k]);
+          for (int j = 0; j < kStrip; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(xw[j + kw], wv[k], acc[j][k]);
         }
       }
     }
-    *reinterpret_cast<uint4*>(y + pos * ldy + v * 8) = pack8(acc);
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j)
+      if (w0 + j < s.w) *reinterpret_cast<uint4*>(y + (rowbase + w0 + j) * ldy + v * 8) = pack8(acc[j]);
   }
 }
 
 // stem weight gradient: partial[block][tap][co] = sum over the block's voxels of dy[pos][co]*x[pos+tap]
-// one thread = one voxel x 4 channels; all 27 taps accumulate in registers.
+// one thread = one strip x 4 channels; all 27 taps accumulate in registers.
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long lddy, int cout,
                   spff_shape s, float* __restrict__ partial) {
   extern __shared__ float red[];  // [warps][27][cout]
   const int c4 = cout / 4;        // channel quads per voxel (must divide 32)
-  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w * c4;
+  const int strips = (s.w + kStrip - 1) / kStrip;
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * strips * c4;
   float acc[27][4];
 #pragma unroll
   for (int t = 0; t < 27; ++t)
@@ -100,31 +133,31 @@ stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__
     for (int k = 0; k < 4; ++k) acc[t][k] = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % c4);
-    const long long pos = i / c4;
-    const int wq = static_cast<int>(pos % s.w);
-    const int hq = static_cast<int>((pos / s.w) % s.h);
-    const int dq = static_cast<int>((pos / (static_cast<long long>(s.w) * s.h)) % s.d);
-    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(dy + pos * lddy + v * 4));
-    const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-    const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    int v, w0, hq, dq;
+    long long rowbase;
+    stem_decode(i, c4, strips, s, v, w0, hq, dq, rowbase);
+    float g[kStrip][4];
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j) {
+      uint2 raw = make_uint2(0, 0);
+      if (w0 + j < s.w) raw = __ldg(reinterpret_cast<const uint2*>(dy + (rowbase + w0 + j) * lddy + v * 4));
+      const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+      const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+      g[j][0] = g01.x; g[j][1] = g01.y; g[j][2] = g23.x; g[j][3] = g23.y;
+    }
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) {
-      const int d2 = dq + kd - 1;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const int h2 = hq + kh - 1;
+        float xw[kStrip + 2];
+        stem_window(x, rowbase, w0, hq, dq, kd, kh, s, xw);
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
-          const int w2 = wq + kw - 1;
-          const bool ok = d2 >= 0 && d2 < s.d && h2 >= 0 && h2 < s.h && w2 >= 0 && w2 < s.w;
-          const float xv =
-              ok ? __ldg(x + pos + (static_cast<long long>(kd - 1) * s.h + (kh - 1)) * s.w + (kw - 1)) : 0.f;
           const int t = (kd * 3 + kh) * 3 + kw;
-          acc[t][0] = fmaf(g01.x, xv, acc[t][0]);
-          acc[t][1] = fmaf(g01.y, xv, acc[t][1]);
-          acc[t][2] = fmaf(g23.x, xv, acc[t][2]);
-          acc[t][3] = fmaf(g23.y, xv, acc[t][3]);
+#pragma unroll
+          for (int j = 0; j < kStrip; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[t][k] = fmaf(g[j][k], xw[j + kw], acc[t][k]);
         }
       }
     }
@@ -370,6 +403,186 @@ ce_kernel(const float* __restrict__ logits, const void* __restrict__ labels, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused training head: 1x1x1 conv (models.py:674) + cross entropy / confusion tally
+// (helpers.py:782-803, 668-725) + their backward, in ONE pass over the last activation.
+//   logits[k] = b[k] + x . w[k]            (registers only - the [N,K,D,H,W] logits are never stored)
+//   acc += nll, counts += valid, confusion[label][argmax] += 1
+//   dl[k] = (softmax[k] - [k == label]) * gscale / n_valid   (0 on ignored voxels)
+//   dx = dl . w  (bf16),   partial dW[k][c] = sum dl[k] x[c],   partial db[k] = sum dl[k]
+// One thread = one voxel for the per-voxel math (weights broadcast from constant memory); the
+// outer product for dW is transposed through shared memory so that lane c owns column c of dW
+// (13 accumulators) and sweeps the 32 voxels of its warp: 1 bf16 + 4 broadcast float4 loads per
+// 13 FMAs. Traffic: 64 B read + 64 B written per voxel (+ label), against 52 B/voxel of fp32 logits
+// written and read three times by the unfused sequence.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHeadLossWarps = 8;
+constexpr int kHeadLossBlocksPerSm = 2;
+
+template <typename LabelT>
+__global__ void __launch_bounds__(kHeadLossWarps * 32, kHeadLossBlocksPerSm)
+head_loss_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const void* __restrict__ labels, int ignore_index,
+                 int K, long long total, const unsigned long long* __restrict__ n_valid,
+                 const float* __restrict__ gscale, double* __restrict__ acc, unsigned long long* __restrict__ counts,
+                 unsigned long long* __restrict__ confusion, __nv_bfloat16* __restrict__ dx, long long lddx,
+                 float* __restrict__ partial /* [block][K*32 + K] */) {
+  // 32 KB: per-warp transpose tiles; re-used as the block-reduction scratch once the loop is done
+  __shared__ __align__(16) unsigned char sraw[kHeadLossWarps * 32 * (kHeadC * 2 + kMaxK * 4)];
+  auto sx = reinterpret_cast<__nv_bfloat16(*)[32][kHeadC]>(sraw);                                   // 16 KB
+  auto sdl = reinterpret_cast<float(*)[32][kMaxK]>(sraw + kHeadLossWarps * 32 * kHeadC * 2);       // 16 KB
+  auto sred = reinterpret_cast<float(*)[kMaxK * kHeadC + kMaxK]>(sraw);                             // 16.5 KB
+  static_assert(sizeof(float) * kHeadLossWarps * (kMaxK * kHeadC + kMaxK) <= sizeof(sraw), "reduction scratch");
+  __shared__ unsigned int s_conf[kMaxK * kMaxK];
+  __shared__ float s_nll[kHeadLossWarps];
+  __shared__ unsigned int s_cnt[kHeadLossWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) s_conf[i] = 0;
+  __syncthreads();
+  const unsigned long long nv = n_valid[0];
+  const float scale = (nv > 0 ? 1.f / static_cast<float>(nv) : 0.f) * (gscale ? gscale[0] : 1.f);
+  float dw[kMaxK], db[kMaxK];
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) dw[k] = db[k] = 0.f;
+  float nll_sum = 0.f;
+  unsigned int cnt = 0;
+  const long long ntiles = (total + 31) / 32;
+  for (long long tile = static_cast<long long>(blockIdx.x) * kHeadLossWarps + warp; tile < ntiles;
+       tile += static_cast<long long>(gridDim.x) * kHeadLossWarps) {
+    const long long pos = tile * 32 + lane;
+    const bool inb = pos < total;
+    uint4 raw[kHeadC / 8];
+    float xv[kHeadC];
+#pragma unroll
+    for (int v = 0; v < kHeadC / 8; ++v) {
+      raw[v] = inb ? __ldg(reinterpret_cast<const uint4*>(x + pos * ldx) + v) : make_uint4(0, 0, 0, 0);
+      float f[8];
+      unpack8(raw[v], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[v * 8 + i] = f[i];
+    }
+    const int lab = inb ? static_cast<int>(static_cast<const LabelT*>(labels)[pos]) : ignore_index;
+    const bool valid = inb && lab != ignore_index;
+    float l[kMaxK];
+    float mx = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+      if (k < K) {
+        float a = c_head_b[k];
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) a = fmaf(xv[c], c_head_w[k * kHeadC + c], a);
+        l[k] = a;
+        if (a > mx) {
+          mx = a;
+          arg = k;
+        }
+      }
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k)
+      if (k < K) {
+        l[k] = __expf(l[k] - mx);   // l[] now holds exp(logit - max); the label's logit is recovered below
+        se += l[k];
+      }
+    const float inv = 1.f / se;
+    if (valid) {
+      float el = 1.f;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        if (k < K && k == lab) el = l[k];
+      nll_sum += __logf(se) - __logf(el);
+      ++cnt;
+      if (lab >= 0 && lab < K) atomicAdd(&s_conf[lab * K + arg], 1u);
+    }
+    float o[kHeadC];
+#pragma unroll
+    for (int c = 0; c < kHeadC; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxK; ++k) {
+      float g = 0.f;
+      if (k < K && valid) g = (l[k] * inv - (k == lab ? 1.f : 0.f)) * scale;
+      l[k] = g;   // l[] now holds d(logits)
+      if (k < K) {
+        db[k] += g;
+#pragma unroll
+        for (int c = 0; c < kHeadC; ++c) o[c] = fmaf(g, c_head_w[k * kHeadC + c], o[c]);
+      }
+    }
+    if (inb && dx) {
+#pragma unroll
+      for (int v = 0; v < kHeadC / 8; ++v) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = o[v * 8 + i];
+        *reinterpret_cast<uint4*>(dx + pos * lddx + v * 8) = pack8(f);
+      }
+    }
+    // transpose through shared memory: lane c accumulates dW[:, c] over the warp's 32 voxels
+#pragma unroll
+    for (int v = 0; v < kHeadC / 8; ++v) *reinterpret_cast<uint4*>(&sx[warp][lane][v * 8]) = raw[v];
+#pragma unroll
+    for (int v = 0; v < kMaxK / 4; ++v)
+      *reinterpret_cast<float4*>(&sdl[warp][lane][v * 4]) = make_float4(l[v * 4], l[v * 4 + 1], l[v * 4 + 2], l[v * 4 + 3]);
+    __syncwarp();
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const float xs = __bfloat162float(sx[warp][j][lane]);
+      float d[kMaxK];
+#pragma unroll
+      for (int v = 0; v < kMaxK / 4; ++v) {
+        const float4 t = *reinterpret_cast<const float4*>(&sdl[warp][j][v * 4]);
+        d[v * 4] = t.x;
+        d[v * 4 + 1] = t.y;
+        d[v * 4 + 2] = t.z;
+        d[v * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k)
+        if (k < K) dw[k] = fmaf(d[k], xs, dw[k]);
+    }
+    __syncwarp();
+  }
+  // block reduction: dW columns are already per lane; db and the loss statistics need a warp sum
+  __syncthreads();   // every warp is done with its transpose tiles
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) {
+    if (k < K) {
+      sred[warp][k * kHeadC + lane] = dw[k];
+      float t = db[k];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) sred[warp][kMaxK * kHeadC + k] = t;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nll_sum += __shfl_xor_sync(0xffffffffu, nll_sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+    s_nll[warp] = nll_sum;
+    s_cnt[warp] = cnt;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * kHeadC + K; i += blockDim.x) {
+    const int src = i < K * kHeadC ? i : kMaxK * kHeadC + (i - K * kHeadC);
+    float t = 0.f;
+    for (int wv = 0; wv < kHeadLossWarps; ++wv) t += sred[wv][src];
+    partial[static_cast<size_t>(blockIdx.x) * (K * kHeadC + K) + i] = t;
+  }
+  if (threadIdx.x == 0) {
+    double t = 0;
+    unsigned long long c = 0;
+    for (int wv = 0; wv < kHeadLossWarps; ++wv) {
+      t += s_nll[wv];
+      c += s_cnt[wv];
+    }
+    atomicAdd(acc, t);
+    atomicAdd(counts, c);
+  }
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+    if (s_conf[i]) atomicAdd(confusion + i, static_cast<unsigned long long>(s_conf[i]));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam semantics, no weight decay / amsgrad)
 // ---------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -551,6 +764,47 @@ int spff_ce_grad(const float* logits, const void* labels, int label_bytes, int i
   else
     spff::ce_kernel<long long, true><<<grid, 256, 0, st>>>(logits, labels, ignore_index, k, dhw, total, nullptr,
                                                            nullptr, nullptr, nv, gscale, dlogits);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+size_t spff_head_loss_workspace(int k) {
+  return static_cast<size_t>(spff::num_sms()) * spff::kHeadLossBlocksPerSm * (k * spff::kHeadC + k) * sizeof(float);
+}
+
+int spff_head_loss_fused(const void* x, long long ldx, int cin, const float* w, const float* b, const void* labels,
+                         int label_bytes, int ignore_index, int k, spff_shape s, const long long* n_valid,
+                         const float* gscale, double* acc, long long* counts, long long* confusion, void* dx,
+                         long long lddx, float* dw, float* db, float beta, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(x && w && b && labels && n_valid && acc && counts && confusion && dw && db && workspace,
+               "head_loss_fused: null pointer");
+  SPFF_REQUIRE(label_bytes == 1 || label_bytes == 8, "head_loss_fused: labels must be uint8 or int64");
+  SPFF_REQUIRE(ldx >= cin && ldx % 8 == 0 && (!dx || (lddx >= cin && lddx % 8 == 0)), "head_loss_fused: bad channel pitch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int e = spff::upload_head(w, b, k, cin, st);
+  if (e) return e;
+  if (workspace_bytes < spff_head_loss_workspace(k)) {
+    spff::set_error("head_loss_fused: workspace too small");
+    return SPFF_ERR_WORKSPACE;
+  }
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * s.w;
+  const int blocks = spff::num_sms() * spff::kHeadLossBlocksPerSm;
+  auto nv = reinterpret_cast<const unsigned long long*>(n_valid);
+  auto cnt = reinterpret_cast<unsigned long long*>(counts);
+  auto conf = reinterpret_cast<unsigned long long*>(confusion);
+  if (label_bytes == 1)
+    spff::head_loss_kernel<uint8_t><<<blocks, spff::kHeadLossWarps * 32, 0, st>>>(
+        static_cast<const bf16*>(x), ldx, labels, ignore_index, k, total, nv, gscale, acc, cnt, conf,
+        static_cast<bf16*>(dx), lddx, static_cast<float*>(workspace));
+  else
+    spff::head_loss_kernel<long long><<<blocks, spff::kHeadLossWarps * 32, 0, st>>>(
+        static_cast<const bf16*>(x), ldx, labels, ignore_index, k, total, nv, gscale, acc, cnt, conf,
+        static_cast<bf16*>(dx), lddx, static_cast<float*>(workspace));
+  const int tot = k * spff::kHeadC + k;
+  spff::head_bwd_reduce_kernel<<<(tot + 127) / 128, 128, 0, st>>>(static_cast<const float*>(workspace), blocks, k, beta,
+                                                                 dw, db);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -59,7 +59,7 @@ _PROTOTYPES = {
     "spff_norm_act_reduce": [_P, _LL, _P, _P, c_int, Shape, c_float, _P],
     "spff_norm_act_affine_apply": [_P, _LL, _P, _P, _P, _P, _LL, _P, _LL, c_int, Shape, c_float, _P],
     "spff_gate_micro_fwd": [_P] * 8 + [c_int, c_int, c_int, Shape, _P, _P, _P],
-    "spff_norm_act_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, c_int, Shape, c_float, _P],
+    "spff_norm_act_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, c_int, Shape, c_float, c_int, _P],
     "spff_gate_micro_bwd": [_P] * 11 + [c_int, c_int, c_int, Shape] + [_P] * 12 + [_P],
     "spff_norm_act_bwd_apply": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _LL, c_int, Shape, c_float, _P],
     "spff_maxpool_bwd_add": [_P, _LL, _P, _LL, _P, _LL, c_int, Shape, c_int, _P],
@@ -69,11 +69,14 @@ _PROTOTYPES = {
     "spff_head_bwd": [_P, _P, _LL, c_int, _P, _P, _LL, _P, _P, c_float, c_int, Shape, _P, c_size_t, _P],
     "spff_ce_confusion": [_P, _P, c_int, c_int, c_int, Shape, _P, _P, _P, _P],
     "spff_ce_grad": [_P, _P, c_int, c_int, c_int, Shape, _P, _P, _P, _P],
+    "spff_head_loss_workspace": [c_int],
+    "spff_head_loss_fused": [_P, _LL, c_int, _P, _P, _P, c_int, c_int, c_int, Shape, _P, _P, _P, _P, _P, _P, _LL, _P, _P,
+                             c_float, _P, c_size_t, _P],
     "spff_adam_step": [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_int, c_float, _P],
 }
 
 _SIZE_T_FUNCS = {"spff_conv3d_k3_wgrad_workspace", "spff_conv3d_stem_wgrad_workspace",
-                 "spff_convt_k122_wgrad_workspace", "spff_head_bwd_workspace"}
+                 "spff_convt_k122_wgrad_workspace", "spff_head_bwd_workspace", "spff_head_loss_workspace"}
 
 
 def _declare():

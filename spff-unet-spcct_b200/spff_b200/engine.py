@@ -136,7 +136,9 @@ class _GroupBuffers:
         self.coef = {f"{b}.{j}": torch.empty(n, self.C[_LEVEL[b]], 4, device=device) for b in BLOCKS for j in (1, 2)}
         self.P = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
         self.Q = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
-        self.logits = torch.empty(n, cfg.num_classes, d, h, w, device=device)
+        self._logits_shape = (n, cfg.num_classes, d, h, w)
+        self._logits = None
+        self._device = device
         self.x_in: Optional[torch.Tensor] = None   # fp32 [n,1,d,h,w] network input of this group
         if train:
             self.dcat = {l: bf(*self.HW[l], 2 * self.C[l]) for l in (1, 2, 3)}
@@ -158,10 +160,12 @@ class _GroupBuffers:
             self.dSa = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
             self.Pout = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
 
-    def dlogits(self) -> torch.Tensor:
-        if getattr(self, "_dlogits", None) is None:
-            self._dlogits = torch.empty_like(self.logits)
-        return self._dlogits
+    @property
+    def logits(self) -> torch.Tensor:
+        """fp32 [n,K,d,h,w] scratch, allocated on first use (the fused training step never needs it)."""
+        if self._logits is None:
+            self._logits = torch.empty(self._logits_shape, device=self._device)
+        return self._logits
 
     def shape(self, level: int) -> Shape:
         hh, ww = self.HW[level]
@@ -363,7 +367,7 @@ class SpffEngine:
         t1, t2 = B.t1[l], B.t2[l]
         # tail + IN2 + lrelu backward
         R2 = B.b32.get(B.idx[f"{b}.R2"])
-        ops.norm_act_bwd_reduce(dout, B.x2[b], B.coef[f"{b}.2"], R2, c, SLOPE)
+        ops.norm_act_bwd_reduce(dout, B.x2[b], B.coef[f"{b}.2"], R2, c, SLOPE, plain=(flags == 0))
         S = B.f32.get(B.idx[f"{b}.S"]) if flags else None
         dse = None
         if flags & GATE_CHANSE:
@@ -381,7 +385,7 @@ class SpffEngine:
         ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.2"][1], t2, c)
         # IN1 + lrelu backward
         R1 = B.b32.get(B.idx[f"{b}.R1"])
-        ops.norm_act_bwd_reduce(t2, B.x1[b], B.coef[f"{b}.1"], R1, c, SLOPE)
+        ops.norm_act_bwd_reduce(t2, B.x1[b], B.coef[f"{b}.1"], R1, c, SLOPE, plain=True)
         ops.gate_micro_bwd(R1, None, B.coef[f"{b}.1"], p[f"{b}.{cn1}.1.weight"], None, None, None, None, 0, c, shp,
                            B.bcoef[f"{b}.1"], None, None, G[f"{b}.{cn1}.1.weight"], G[f"{b}.{cn1}.1.bias"], None, None,
                            None, None)
@@ -393,14 +397,17 @@ class SpffEngine:
             ops.conv3d_k3_wgrad(xin, cin, t1, c, G[f"{b}.{cn1}.0.weight"], 1.0)
             ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.1"][1], dxin, cin)
 
-    def backward_group(self, B: _GroupBuffers, T: GateTables, G: Dict[str, torch.Tensor], dlogits: torch.Tensor):
+    def backward_group(self, B: _GroupBuffers, T: GateTables, G: Dict[str, torch.Tensor],
+                       dlogits: Optional[torch.Tensor]):
         """Accumulates (+=) every parameter gradient of this group into the fp32 tensors of `G`
-        (shaped like the parameters). dlogits: fp32 [n,K,d,h,w]."""
+        (shaped like the parameters). dlogits: fp32 [n,K,d,h,w], or None when the fused head/loss
+        kernel already left the head's input gradient in B.gout[1] (and its dW/db in G)."""
         p = self.params()
         B.b32.zero()
         B.b64.zero()
-        ops.head_bwd(dlogits, B.out["dec1"], p["out.weight"], B.gout[1], G["out.weight"].view(-1, self.cfg.base),
-                     G["out.bias"], 1.0)
+        if dlogits is not None:
+            ops.head_bwd(dlogits, B.out["dec1"], p["out.weight"], B.gout[1], G["out.weight"].view(-1, self.cfg.base),
+                         G["out.bias"], 1.0)
         for l, up, dec, below in ((1, "up1", "dec1", "dec2"), (2, "up2", "dec2", "dec3"), (3, "up3", "dec3", "bott")):
             cu = B.C[l]
             self._block_bwd(B, T, G, dec, B.gout[l], B.cat[l], B.dcat[l])
@@ -493,13 +500,15 @@ class SpffEngine:
         self.refresh_weights()
         T = GateTables(self.cfg, self.params(), d, need_grad=True)
         n_valid = (labels != ignore_index).sum().reshape(1)     # the CE normaliser spans the whole batch
+        p = self.params()
         for lo, hi in self._groups(bsz, group):
             B = self.buffers(hi - lo, d, h, w, x.device, train=True)
-            self.forward_group(B, T, x[lo:hi], head="logits")
-            ops.ce_confusion(B.logits, labels[lo:hi], ignore_index, tally.nll, tally.count, tally.confusion)
-            dlogits = B.dlogits()
-            ops.ce_grad(B.logits, labels[lo:hi], ignore_index, n_valid, None, dlogits)
-            self.backward_group(B, T, G, dlogits)
+            self.forward_group(B, T, x[lo:hi], head="none")
+            # head + CE + confusion + their backward in one pass; the logits never reach memory
+            ops.head_loss_fused(B.out["dec1"], p["out.weight"], p["out.bias"], labels[lo:hi], ignore_index, n_valid, None,
+                                tally.nll, tally.count, tally.confusion, B.gout[1],
+                                G["out.weight"].view(-1, self.cfg.base), G["out.bias"], 1.0)
+            self.backward_group(B, T, G, None)
         T.finish(G)
 
 

@@ -186,10 +186,12 @@ def gate_micro_fwd(S, g1, bt, kfg, se, flags, c, shape, P, Q):
          shape, ptr(P), ptr(Q), stream_ptr())
 
 
-def norm_act_bwd_reduce(dout, x, coef, R, c, slope):
+def norm_act_bwd_reduce(dout, x, coef, R, c, slope, plain=False):
+    """plain=True: only the two sums the gate-free InstanceNorm + LeakyReLU backward needs."""
     s, lddo = _view(dout, c)
     _, ldx = _view(x, c)
-    call("spff_norm_act_bwd_reduce", ptr(dout), lddo, ptr(x), ldx, ptr(coef), ptr(R), c, s, float(slope), stream_ptr())
+    call("spff_norm_act_bwd_reduce", ptr(dout), lddo, ptr(x), ldx, ptr(coef), ptr(R), c, s, float(slope), int(plain),
+         stream_ptr())
 
 
 def gate_micro_bwd(R, S, coef, gamma, g1, bt, kfg, se, flags, c, shape, bcoef, dSa, Pout, dgamma, dbeta, dg1, dbt, dkfg,
@@ -263,6 +265,18 @@ def ce_grad(logits, labels, ignore_index, n_valid, gscale, dlogits):
     n, k, d, h, w = logits.shape
     call("spff_ce_grad", ptr(logits), ptr(labels), _label_bytes(labels), int(ignore_index), k, Shape(n, d, h, w),
          ptr(n_valid), ptr(gscale), ptr(dlogits), stream_ptr())
+
+
+def head_loss_fused(x, w, b, labels, ignore_index, n_valid, gscale, acc, counts, confusion, dx, dw, db, beta=0.0):
+    """Fused training head (no logits in memory): loss statistics += , dx / dw / db of the batch-mean CE."""
+    k = w.shape[0]
+    s, ldx = _view(x, 32)
+    lddx = _view(dx, 32)[1] if dx is not None else 0
+    assert labels.is_contiguous() and labels.numel() == s.n * s.d * s.h * s.w
+    ws = workspace(int(_lib.lib.spff_head_loss_workspace(k)), x.device)
+    call("spff_head_loss_fused", ptr(x), ldx, 32, ptr(w), ptr(b), ptr(labels), _label_bytes(labels), int(ignore_index), k, s,
+         ptr(n_valid), ptr(gscale), ptr(acc), ptr(counts), ptr(confusion), ptr(dx), lddx, ptr(dw), ptr(db), float(beta),
+         ptr(ws), ws.numel(), stream_ptr())
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):

@@ -316,6 +316,45 @@ def test_head_and_loss():
     assert rel(db, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize("n,d,h,w,dtype", [(2, 5, 12, 12, torch.int64), (1, 5, 7, 9, torch.uint8), (3, 5, 32, 32, torch.int64)])
+def test_head_loss_fused(n, d, h, w, dtype):
+    """Fused head + CE + confusion + backward == F.conv3d -> F.cross_entropy -> autograd (fp32)."""
+    from spff_b200 import ops
+    from oracle import spff_oracle as O
+    k = 13
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(1)
+    xb = pm(torch.randn(n, 32, d, h, w, device="cuda"), ld=64)      # a channel slice of a wider buffer
+    wt = (torch.randn(k, 32, 1, 1, 1, device="cuda") * 0.5).requires_grad_()
+    b = (torch.randn(k, device="cuda") * 0.1).requires_grad_()
+    labels = torch.randint(0, k, (n, d, h, w), device="cuda")
+    labels[torch.rand(n, d, h, w, device="cuda") < 0.1] = 255
+    xr = ncdhw(xb).requires_grad_()
+    logits = F.conv3d(xr, wt, b)
+    ce = F.cross_entropy(logits, labels, ignore_index=255)
+    (ce * 0.5).backward()
+    acc = torch.zeros(1, dtype=torch.float64, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    conf = torch.zeros(k, k, dtype=torch.int64, device="cuda")
+    n_valid = (labels != 255).sum().reshape(1)
+    gscale = torch.tensor([0.5], device="cuda")
+    dx = torch.full((n, d, h, w, 64), float("nan"), dtype=torch.bfloat16, device="cuda")[..., :32]
+    dw = torch.ones(k, 32, device="cuda"); db = torch.ones(k, device="cuda")
+    ops.head_loss_fused(xb, wt.detach(), b.detach(), labels.to(dtype), 255, n_valid, gscale, acc, cnt, conf, dx, dw, db, 1.0)
+    assert int(cnt) == int(n_valid)
+    assert abs(float(acc) / int(cnt) - float(ce)) < 1e-5
+    assert (conf.cpu().numpy() == O.confusion(logits.argmax(1).cpu(), labels.cpu(), k, 255)).all()
+    assert rel(ncdhw(dx), xr.grad) < 5e-3
+    assert rel(dw - 1, wt.grad.reshape(k, 32)) < 1e-4
+    assert rel(db - 1, b.grad) < 1e-4
+    # dx optional, beta = 0 overwrites
+    dw2 = torch.full((k, 32), float("nan"), device="cuda"); db2 = torch.full((k,), float("nan"), device="cuda")
+    acc.zero_(); cnt.zero_(); conf.zero_()
+    ops.head_loss_fused(xb, wt.detach(), b.detach(), labels.to(dtype), 255, n_valid, gscale, acc, cnt, conf, None, dw2, db2, 0.0)
+    assert rel(dw2, wt.grad.reshape(k, 32)) < 1e-4 and rel(db2, b.grad) < 1e-4
+
+
 def test_adam():
     from spff_b200 import ops
     torch.manual_seed(0)
