@@ -100,7 +100,7 @@ __device__ __forceinline__ bool fast_reduce_ok(int c8) { return c8 <= 32 && (c8 
 // InstanceNorm statistics: stats[n][c] += {sum x, sum x^2} over the block's positions (double).
 // grid = (chunks, d, n)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) in_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
+__global__ void __launch_bounds__(kBlock, 5) in_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ld,
                                                           PlaneGrid g, int d, double* __restrict__ stats, int c) {
   extern __shared__ float red[];
   const int n = blockIdx.z, dd = blockIdx.y;
@@ -523,6 +523,210 @@ maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ dpool, long long ldp, c
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward passes, 4 channels per thread (8-byte accesses). Half the per-thread state of the
+// 8-channel kernels above -> 3-4 resident blocks per SM instead of 2, which is what these
+// instruction-heavy streaming kernels need to cover HBM latency. cv = c / 4 vectors per position,
+// a power of two <= 256; thread -> (row r = tid / cv, vector v = tid % cv).
+// ---------------------------------------------------------------------------------------------
+struct PlaneGrid4 {
+  int cv, rpi, hw, chunk;
+};
+
+__device__ __forceinline__ void unpack4(const uint2& v, float (&f)[4]) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ uint2 pack4(const float (&f)[4]) {
+  uint2 v;
+  *reinterpret_cast<__nv_bfloat162*>(&v.x) = __floats2bfloat162_rn(f[0], f[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&v.y) = __floats2bfloat162_rn(f[2], f[3]);
+  return v;
+}
+__device__ __forceinline__ uint2 ldg8(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+
+// rows sharing a warp fold with shuffles, row-warps meet in shared memory ([row-warp][vec][NV]);
+// afterwards reduce_cv_fetch(idx) returns output element idx = vec * NV + i. red: 8*32*NV floats.
+template <int NV>
+__device__ __forceinline__ void reduce_cv(float (&v)[NV], float* red, int cv) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = cv < 32 ? cv : 32, wpr = cv > 32 ? cv / 32 : 1;
+  for (int off = 16; off >= cv; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+  }
+  if (lane < L) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[((warp / wpr) * (wpr * L) + (warp % wpr) * L + lane) * NV + i] = v[i];
+  }
+  __syncthreads();
+}
+template <int NV>
+__device__ __forceinline__ float reduce_cv_fetch(const float* red, int cv, int idx) {
+  const int L = cv < 32 ? cv : 32, wpr = cv > 32 ? cv / 32 : 1;
+  const int nrw = (kBlock / 32) / wpr, span = wpr * L * NV;
+  float t = 0.f;
+  for (int w = 0; w < nrw; ++w) t += red[w * span + idx];
+  return t;
+}
+
+template <bool PLAIN>
+__global__ void __launch_bounds__(kBlock, PLAIN ? 4 : 3)
+norm_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ x,
+                            long long ldx, const float* __restrict__ coef, float* __restrict__ R, PlaneGrid4 g, int d,
+                            int c, float slope) {
+  extern __shared__ float red[];
+  constexpr int NK = PLAIN ? 2 : 6;
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.cv, r = threadIdx.x / g.cv;
+  const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  float A[4], B[4], Mn[4], Rs[4];
+  {
+    const float4* cf = reinterpret_cast<const float4*>(coef) + static_cast<long long>(n) * c + v * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(cf + i);
+      A[i] = t.x; B[i] = t.y; Mn[i] = t.z; Rs[i] = t.w;
+    }
+  }
+  float acc[NK][4];
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+  constexpr int U = 4;   // 4 x (x, dout) 8-byte loads in flight per thread
+  for (int p = p0 + r; p < p1; p += U * g.rpi) {
+    uint2 rx[U], rg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = p + u * g.rpi < p1;
+      rx[u] = ok ? ldg8(x + (base + p + u * g.rpi) * ldx + v * 4) : make_uint2(0, 0);
+      rg[u] = ok ? ldg8(dout + (base + p + u * g.rpi) * lddo + v * 4) : make_uint2(0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float f[4], go[4];
+      unpack4(rx[u], f);
+      unpack4(rg[u], go);   // rows past the chunk carry dout = 0: nothing reaches slots 0, 1, 2, 4
+      const float live = (p + u * g.rpi < p1) ? 1.f : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float z = fmaf(f[i], A[i], B[i]);
+        const float m = z > 0.f ? 1.f : slope;
+        const float xh = (f[i] - Mn[i]) * Rs[i];
+        const float gm = go[i] * m;
+        if (PLAIN) {
+          acc[0][i] += gm;
+          acc[1][i] = fmaf(gm, xh, acc[1][i]);
+        } else {
+          const float ml = m * live;
+          acc[0][i] = fmaf(gm, z, acc[0][i]);
+          acc[1][i] += go[i];
+          acc[2][i] += gm;
+          acc[3][i] += ml;
+          acc[4][i] = fmaf(gm, xh, acc[4][i]);
+          acc[5][i] = fmaf(ml, xh, acc[5][i]);
+        }
+      }
+    }
+  }
+  float* Rp = R + (static_cast<long long>(n) * d + dd) * c * 6;
+  const int nout = (g.cv < kBlock ? g.cv : kBlock) * 4;   // = c
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int slot = PLAIN ? (k == 0 ? 2 : 4) : k;
+    reduce_cv<4>(acc[k], red, g.cv);
+    for (int idx = threadIdx.x; idx < nout; idx += kBlock) atomicAdd(Rp + idx * 6 + slot, reduce_cv_fetch<4>(red, g.cv, idx));
+    __syncthreads();
+  }
+}
+
+template <bool AFFINE>
+__global__ void __launch_bounds__(kBlock, 4)
+norm_act_bwd_apply4_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ x,
+                           long long ldx, const float* __restrict__ coef, const float* __restrict__ bcoef,
+                           const float* __restrict__ P, const float* __restrict__ dSa, __nv_bfloat16* __restrict__ dx,
+                           long long lddx, PlaneGrid4 g, int d, int c, float slope) {
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.cv, r = threadIdx.x / g.cv;
+  const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  float A[4], B[4], K1[4], K1d[4], K2[4], K3[4];
+  {
+    const float4* cf = reinterpret_cast<const float4*>(coef) + static_cast<long long>(n) * c + v * 4;
+    const float4* bf = reinterpret_cast<const float4*>(bcoef) + static_cast<long long>(n) * c + v * 4;
+    float4 pv = make_float4(1.f, 1.f, 1.f, 1.f), dv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (AFFINE) {
+      const long long pq = (static_cast<long long>(n) * d + dd) * c + v * 4;
+      pv = __ldg(reinterpret_cast<const float4*>(P + pq));
+      dv = __ldg(reinterpret_cast<const float4*>(dSa + pq));
+    }
+    const float Pv[4] = {pv.x, pv.y, pv.z, pv.w}, Dv[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(cf + i);   // {A, B, mean, rstd}
+      const float4 u = __ldg(bf + i);   // {c1, c2, c3, -}
+      A[i] = t.x;
+      B[i] = t.y;
+      K1[i] = u.x * Pv[i];
+      K1d[i] = u.x * Dv[i];
+      K2[i] = -u.x * u.z * t.w;
+      K3[i] = u.x * (u.z * t.w * t.z - u.y);
+    }
+  }
+  constexpr int U = 4;
+  for (int p = p0 + r; p < p1; p += U * g.rpi) {
+    uint2 rx[U], rg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p + u * g.rpi < p1) {
+        rx[u] = ldg8(x + (base + p + u * g.rpi) * ldx + v * 4);
+        rg[u] = ldg8(dout + (base + p + u * g.rpi) * lddo + v * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p + u * g.rpi < p1) {
+        float f[4], go[4];
+        unpack4(rx[u], f);
+        unpack4(rg[u], go);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float z = fmaf(f[i], A[i], B[i]);
+          const float m = z > 0.f ? 1.f : slope;
+          f[i] = fmaf(m, fmaf(K1[i], go[i], K1d[i]), fmaf(K2[i], f[i], K3[i]));
+        }
+        *reinterpret_cast<uint2*>(dx + (base + p + u * g.rpi) * lddx + v * 4) = pack4(f);
+      }
+    }
+  }
+}
+
+// grid for the 4-channel kernels; returns false when the channel count does not fit them
+bool make_grid4(int c, long long hw, spff_shape s, PlaneGrid4* g, dim3* grid) {
+  if (c % 4 != 0 || c <= 0) return false;
+  const int cv = c / 4;
+  if (cv > kBlock || (cv & (cv - 1)) != 0 || s.d > 65535 || s.n > 65535) return false;
+  g->cv = cv;
+  g->rpi = kBlock / cv;
+  g->hw = static_cast<int>(hw);
+  // ~6 waves of blocks over the device (3-4 resident per SM), at least 8 iterations per thread
+  const long long planes = static_cast<long long>(s.n) * s.d;
+  long long want_chunks = (24LL * num_sms() + planes - 1) / planes;
+  if (want_chunks < 1) want_chunks = 1;
+  long long chunk = (hw + want_chunks - 1) / want_chunks;
+  const long long min_chunk = 8LL * g->rpi;
+  if (chunk < min_chunk) chunk = min_chunk;
+  chunk = ((chunk + g->rpi - 1) / g->rpi) * g->rpi;
+  g->chunk = static_cast<int>(chunk);
+  *grid = dim3(static_cast<unsigned>((hw + chunk - 1) / chunk), s.d, s.n);
+  return true;
+}
+
 int make_grid(int c, long long hw, spff_shape s, PlaneGrid* g, dim3* grid) {
   if (c % 8 != 0 || c <= 0 || c > 8 * kBlock) {
     set_error("channel count %d must be a multiple of 8 and <= %d", c, 8 * kBlock);
@@ -652,6 +856,21 @@ int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, lo
   SPFF_ENTRY_CHECK();
   PlaneGrid g;
   dim3 grid;
+  {
+    spff::PlaneGrid4 g4;
+    if (spff::make_grid4(c, static_cast<long long>(s.h) * s.w, s, &g4, &grid)) {
+      cudaStream_t st4 = static_cast<cudaStream_t>(stream);
+      const size_t smem = 8 * 32 * 4 * sizeof(float);
+      if (plain)
+        spff::norm_act_bwd_reduce4_kernel<true><<<grid, kBlock, smem, st4>>>(
+            static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g4, s.d, c, slope);
+      else
+        spff::norm_act_bwd_reduce4_kernel<false><<<grid, kBlock, smem, st4>>>(
+            static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g4, s.d, c, slope);
+      SPFF_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
   if (e) return e;
   if (plain)
@@ -671,9 +890,24 @@ int spff_norm_act_bwd_apply(const void* dout, long long lddo, const void* x, lon
   SPFF_REQUIRE((P == nullptr) == (dSa == nullptr), "norm_act_bwd_apply: P and dSa must both be given or both be NULL");
   PlaneGrid g;
   dim3 grid;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    spff::PlaneGrid4 g4;
+    if (spff::make_grid4(c, static_cast<long long>(s.h) * s.w, s, &g4, &grid)) {
+      if (P)
+        spff::norm_act_bwd_apply4_kernel<true><<<grid, kBlock, 0, st>>>(
+            static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, bcoef, P, dSa,
+            static_cast<bf16*>(dx), lddx, g4, s.d, c, slope);
+      else
+        spff::norm_act_bwd_apply4_kernel<false><<<grid, kBlock, 0, st>>>(
+            static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, bcoef, P, dSa,
+            static_cast<bf16*>(dx), lddx, g4, s.d, c, slope);
+      SPFF_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
   if (e) return e;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (P)
     spff::norm_act_bwd_apply_kernel<true><<<grid, kBlock, 0, st>>>(static_cast<const bf16*>(dout), lddo,
                                                                   static_cast<const bf16*>(x), ldx, coef, bcoef, P, dSa,
