@@ -143,17 +143,22 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 
   if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // All 32 lanes run the control flow, so every address / coordinate is provably warp-uniform
+    // and stays in uniform registers; one elected lane issues the TMA instructions.
+    const bool leader = elect_one() != 0;
+    {
       int s = 0, ws = 0;
       uint32_t ph = 0, wph = 0;
       if (RES) {
         const int cb = blockIdx.x % p.ncb;
         for (int kh = 0; kh < 3; ++kh) {
-          mbar_expect_tx(&wfull[kh], L::kWBytes);
           const int wrow = (cb * 3 + kh) * 3 * kN;
+          if (leader) {
+            mbar_expect_tx(&wfull[kh], L::kWBytes);
 #pragma unroll
-          for (int kd = 0; kd < 3; ++kd)
-            tma_load_2d(sW + kh * L::kWBytes + kd * L::kWBlock, &tmap_w, &wfull[kh], 0, wrow + kd * kN);
+            for (int kd = 0; kd < 3; ++kd)
+              tma_load_2d(sW + kh * L::kWBytes + kd * L::kWBlock, &tmap_w, &wfull[kh], 0, wrow + kd * kN);
+          }
         }
       }
       for (long long item = item0; item < nitems; item += istep) {
@@ -167,8 +172,10 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           for (int dp = dlo; dp <= dhi; ++dp) {
             for (int kh = 0; kh < 3; ++kh) {
               mbar_wait(&empty[s], ph ^ 1);
-              mbar_expect_tx(&full[s], L::kABytes);
-              tma_load_4d(sA + s * L::kABytes, &tmap_x, &full[s], 0, tq0 + (kh - 1) * p.w, dp, n);
+              if (leader) {
+                mbar_expect_tx(&full[s], L::kABytes);
+                tma_load_4d(sA + s * L::kABytes, &tmap_x, &full[s], 0, tq0 + (kh - 1) * p.w, dp, n);
+              }
               if (++s == L::kStages) {
                 s = 0;
                 ph ^= 1;
@@ -179,19 +186,23 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           for (int kh = 0; kh < 3; ++kh) {
             for (int kc = 0; kc < p.nkc; ++kc) {
               mbar_wait(&wempty[ws], wph ^ 1);
-              mbar_expect_tx(&wfull[ws], L::kWBytes);
               const int wrow = ((cb * 3 + kh) * p.nkc + kc) * 3 * kN;
+              if (leader) {
+                mbar_expect_tx(&wfull[ws], L::kWBytes);
 #pragma unroll
-              for (int kd = 0; kd < 3; ++kd)
-                tma_load_2d(sW + ws * L::kWBytes + kd * L::kWBlock, &tmap_w, &wfull[ws], 0, wrow + kd * kN);
+                for (int kd = 0; kd < 3; ++kd)
+                  tma_load_2d(sW + ws * L::kWBytes + kd * L::kWBlock, &tmap_w, &wfull[ws], 0, wrow + kd * kN);
+              }
               if (++ws == L::kWStages) {
                 ws = 0;
                 wph ^= 1;
               }
               for (int dp = dlo; dp <= dhi; ++dp) {
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], L::kABytes);
-                tma_load_4d(sA + s * L::kABytes, &tmap_x, &full[s], kc * KC, tq0 + (kh - 1) * p.w, dp, n);
+                if (leader) {
+                  mbar_expect_tx(&full[s], L::kABytes);
+                  tma_load_4d(sA + s * L::kABytes, &tmap_x, &full[s], kc * KC, tq0 + (kh - 1) * p.w, dp, n);
+                }
                 if (++s == L::kStages) {
                   s = 0;
                   ph ^= 1;
@@ -204,7 +215,11 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // Warp-uniform control flow (all 32 lanes), one elected lane issues tcgen05.mma / commit: the
+    // descriptors, TMEM addresses and barrier addresses then live in uniform registers instead of
+    // being moved there (R2UR) in front of every instruction by a single divergent thread.
+    const bool leader = elect_one() != 0;
+    {
       int s = 0, ws = 0;
       uint32_t ph = 0, wph = 0;
       uint32_t accpar = 0;  // per accumulator slot: parity of its next acc_empty wait
@@ -212,7 +227,11 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         for (int kh = 0; kh < 3; ++kh) mbar_wait(&wfull[kh], 0);
       }
       // one A stage against the kd blocks at wbase; returns the updated touched mask
-      auto stage_mmas = [&](uint32_t abase, uint32_t wbase, int dp, int d0, int dend, uint32_t touched) -> uint32_t {
+      // descriptors advance by plain additions on the 14-bit (address >> 4) field: the whole dynamic
+      // shared window is < 256 KB, so the field never overflows into its neighbours
+      const uint64_t a_desc0 = smem_desc(desc_hi, smem_u32(sA));
+      const uint64_t w_desc0 = smem_desc(desc_hi, smem_u32(sW));
+      auto stage_mmas = [&](uint64_t adesc, uint64_t wdesc, int dp, int d0, int dend, uint32_t touched) -> uint32_t {
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd) {
           const int dout = dp - (kd - 1);
@@ -226,9 +245,9 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             const uint32_t dcol = tmem_base + j * kN;
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
-              const uint64_t ad = smem_desc(desc_hi, abase + k * 32);
-              const uint64_t bd = smem_desc(desc_hi, wbase + kd * L::kWBlock + k * 32);
-              umma_bf16(dcol, ad, bd, idesc, ((touched >> j) & 1u) | (k > 0 ? 1u : 0u));
+              const uint64_t ad = adesc + static_cast<uint64_t>(k * 2);
+              const uint64_t bd = wdesc + static_cast<uint64_t>(kd * (L::kWBlock >> 4) + k * 2);
+              if (leader) umma_bf16(dcol, ad, bd, idesc, ((touched >> j) & 1u) | (k > 0 ? 1u : 0u));
             }
             touched |= 1u << j;
           }
@@ -248,39 +267,41 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             for (int kh = 0; kh < 3; ++kh) {
               mbar_wait(&full[s], ph);
               tc_fence_after();
-              touched = stage_mmas(smem_u32(sA + s * L::kABytes), smem_u32(sW + kh * L::kWBytes), dp, d0, dend, touched);
-              umma_commit(&empty[s]);
+              touched = stage_mmas(a_desc0 + static_cast<uint64_t>(s * (L::kABytes >> 4)),
+                                   w_desc0 + static_cast<uint64_t>(kh * (L::kWBytes >> 4)), dp, d0, dend, touched);
+              if (leader) umma_commit(&empty[s]);
               if (++s == L::kStages) {
                 s = 0;
                 ph ^= 1;
               }
             }
-            if (dp - 1 >= d0 && dp - 1 < dend) umma_commit(&acc_full[dp - 1 - d0]);
-            if (dp == dhi && dhi < dend) umma_commit(&acc_full[dhi - d0]);
+            if (leader && dp - 1 >= d0 && dp - 1 < dend) umma_commit(&acc_full[dp - 1 - d0]);
+            if (leader && dp == dhi && dhi < dend) umma_commit(&acc_full[dhi - d0]);
           }
         } else {
           for (int kh = 0; kh < 3; ++kh) {
             for (int kc = 0; kc < p.nkc; ++kc) {
               mbar_wait(&wfull[ws], wph);
-              const uint32_t wbase = smem_u32(sW + ws * L::kWBytes);
+              const uint64_t wbase = w_desc0 + static_cast<uint64_t>(ws * (L::kWBytes >> 4));
               for (int dp = dlo; dp <= dhi; ++dp) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                touched = stage_mmas(smem_u32(sA + s * L::kABytes), wbase, dp, d0, dend, touched);
-                umma_commit(&empty[s]);
+                touched = stage_mmas(a_desc0 + static_cast<uint64_t>(s * (L::kABytes >> 4)), wbase, dp, d0, dend, touched);
+                if (leader) umma_commit(&empty[s]);
                 if (++s == L::kStages) {
                   s = 0;
                   ph ^= 1;
                 }
               }
-              umma_commit(&wempty[ws]);
+              if (leader) umma_commit(&wempty[ws]);
               if (++ws == L::kWStages) {
                 ws = 0;
                 wph ^= 1;
               }
             }
           }
-          for (int j = 0; j < dend - d0; ++j) umma_commit(&acc_full[j]);
+          if (leader)
+            for (int j = 0; j < dend - d0; ++j) umma_commit(&acc_full[j]);
         }
       }
     }

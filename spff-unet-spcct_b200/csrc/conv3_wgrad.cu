@@ -115,7 +115,9 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_con
   const uint32_t x_tile_bytes = rows * CIB * 2;
 
   if (warp == 4) {
-    if (lane == 0) {
+    // warp-uniform control flow, one elected lane issues (coordinates stay in uniform registers)
+    const bool leader = elect_one() != 0;
+    {
       int xs = 0, ds = 0;
       uint32_t xph = 0, dph = 0;
       for (long long t = t_begin; t < t_end; ++t) {
@@ -127,21 +129,25 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_con
           const int d0 = pg * p.G;
           const int dend = min(p.d, d0 + p.G);
           mbar_wait(&dyempty[ds], dph ^ 1);
-          mbar_expect_tx(&dyfull[ds], (p.G + 3) * dy_tile_bytes);
-          for (int sl = 0; sl < p.G + 3; ++sl)
-            tma_load_5d(sDy + ds * C::DySet + sl * kSlotBytes, &tmap_dy, &dyfull[ds], cob * COB, w0, h0, d0 - 1 + sl,
-                        n);
+          if (leader) {
+            mbar_expect_tx(&dyfull[ds], (p.G + 3) * dy_tile_bytes);
+            for (int sl = 0; sl < p.G + 3; ++sl)
+              tma_load_5d(sDy + ds * C::DySet + sl * kSlotBytes, &tmap_dy, &dyfull[ds], cob * COB, w0, h0, d0 - 1 + sl,
+                          n);
+          }
           if (++ds == 2) {
             ds = 0;
             dph ^= 1;
           }
           for (int dp = d0; dp < dend; ++dp) {
             mbar_wait(&xempty[xs], xph ^ 1);
-            mbar_expect_tx(&xfull[xs], 3 * x_tile_bytes);
+            if (leader) {
+              mbar_expect_tx(&xfull[xs], 3 * x_tile_bytes);
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-              tma_load_5d(sX + xs * C::XBytes + kw * C::XT, &tmap_x, &xfull[xs], cib * CIB, w0 + kw - 1, h0 + kh - 1, dp,
-                          n);
+              for (int kw = 0; kw < 3; ++kw)
+                tma_load_5d(sX + xs * C::XBytes + kw * C::XT, &tmap_x, &xfull[xs], cib * CIB, w0 + kw - 1, h0 + kh - 1,
+                            dp, n);
+            }
             if (++xs == C::XStages) {
               xs = 0;
               xph ^= 1;
@@ -151,7 +157,8 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_con
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    const bool leader = elect_one() != 0;
+    {
       constexpr uint32_t kSwzA = (COB == 64) ? kSwizzle128 : kSwizzle64;
       constexpr uint32_t kSwzB = (CIB == 64) ? kSwizzle128 : kSwizzle64;
       constexpr uint32_t kSboA = (COB == 64) ? 1024 : 512;
@@ -161,6 +168,9 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_con
       const uint64_t bdesc_hi = make_smem_desc_hi(C::XT, kSboB, kSwzB);
       const uint32_t idesc = make_idesc_bf16(128, C::N, 1, 1);
       const int ksteps = rows / 16;
+      // descriptors advance by additions on the (address >> 4) field (the smem window is < 256 KB)
+      const uint64_t adesc0 = smem_desc(adesc_hi, smem_u32(sDy));
+      const uint64_t bdesc0 = smem_desc(bdesc_hi, smem_u32(sX));
       int xs = 0, ds = 0;
       uint32_t xph = 0, dph = 0;
       uint32_t first = 1;
@@ -170,35 +180,36 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_con
           const int dend = min(p.d, d0 + p.G);
           mbar_wait(&dyfull[ds], dph);
           tc_fence_after();
-          const uint32_t dybase = smem_u32(sDy + ds * C::DySet);
+          const uint64_t dydesc = adesc0 + static_cast<uint64_t>(ds * (C::DySet >> 4));
           for (int dp = d0; dp < dend; ++dp) {
             mbar_wait(&xfull[xs], xph);
             tc_fence_after();
-            const uint32_t xbase = smem_u32(sX + xs * C::XBytes);
+            const uint64_t xdesc = bdesc0 + static_cast<uint64_t>(xs * (C::XBytes >> 4));
 #pragma unroll
             for (int i = 0; i < C::NMMA; ++i) {
-              const uint32_t abase = dybase + (dp - d0 + i * C::SP) * kSlotBytes;
+              uint64_t ad = dydesc + static_cast<uint64_t>((dp - d0 + i * C::SP) * (kSlotBytes >> 4));
+              uint64_t bd = xdesc;
               for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t ad = smem_desc(adesc_hi, abase + ks * 2 * kSboA);
-                const uint64_t bd = smem_desc(bdesc_hi, xbase + ks * 2 * kSboB);
-                umma_bf16(tmem_base + i * C::N, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                if (leader) umma_bf16(tmem_base + i * C::N, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                ad += (2 * kSboA) >> 4;
+                bd += (2 * kSboB) >> 4;
               }
             }
             first = 0;
-            umma_commit(&xempty[xs]);
+            if (leader) umma_commit(&xempty[xs]);
             if (++xs == C::XStages) {
               xs = 0;
               xph ^= 1;
             }
           }
-          umma_commit(&dyempty[ds]);
+          if (leader) umma_commit(&dyempty[ds]);
           if (++ds == 2) {
             ds = 0;
             dph ^= 1;
           }
         }
       }
-      umma_commit(acc_full);
+      if (leader) umma_commit(acc_full);
     }
   } else {
     // epilogue: TMEM -> workspace partials [mma][lane][N]

@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
   };
 
   if (warp == 4) {
-    if (lane == 0) {
+    const bool leader = elect_one() != 0;   // warp-uniform control flow, one elected lane issues
+    {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t bytes = rows * KC * 2 + p.N * KC * 2;
@@ -111,11 +112,13 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
         for (int t = 0; t < p.ntap; ++t) {
           for (int kc = 0; kc < p.nkc; ++kc) {
             mbar_wait(&empty[s], ph ^ 1);
-            mbar_expect_tx(&full[s], bytes);
             uint8_t* st = smem + s * L::kStage;
-            tma_load_5d(st, &maps.a[t], &full[s], kc * KC, w0, h0, dd, n);
             const int blk = (p.nquad > 1 ? qo : t) * p.nkc + kc;
-            tma_load_2d(st + L::kABytes, &maps.b, &full[s], 0, blk * p.N);
+            if (leader) {
+              mbar_expect_tx(&full[s], bytes);
+              tma_load_5d(st, &maps.a[t], &full[s], kc * KC, w0, h0, dd, n);
+              tma_load_2d(st + L::kABytes, &maps.b, &full[s], 0, blk * p.N);
+            }
             if (++s == L::kStages) {
               s = 0;
               ph ^= 1;
@@ -125,11 +128,13 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    const bool leader = elect_one() != 0;
+    {
       constexpr uint32_t kSwz = (KC == 64) ? kSwizzle128 : kSwizzle64;
       constexpr uint32_t kSbo = (KC == 64) ? 1024 : 512;
       const uint64_t desc_hi = make_smem_desc_hi(16, kSbo, kSwz);
       const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
+      const uint64_t desc0 = smem_desc(desc_hi, smem_u32(smem));
       int s = 0;
       uint32_t ph = 0, accph = 0;
       int buf = 0;
@@ -142,21 +147,20 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
         for (int it = 0; it < p.ntap * p.nkc; ++it) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t abase = smem_u32(smem + s * L::kStage);
-          const uint32_t bbase = abase + L::kABytes;
+          const uint64_t ad0 = desc0 + static_cast<uint64_t>(s * (L::kStage >> 4));
+          const uint64_t bd0 = ad0 + (L::kABytes >> 4);
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k) {
-            umma_bf16(dcol, smem_desc(desc_hi, abase + k * 32), smem_desc(desc_hi, bbase + k * 32), idesc,
-                      (first && k == 0) ? 0u : 1u);
+            if (leader) umma_bf16(dcol, ad0 + k * 2, bd0 + k * 2, idesc, (first && k == 0) ? 0u : 1u);
           }
           first = 0;
-          umma_commit(&empty[s]);
+          if (leader) umma_commit(&empty[s]);
           if (++s == L::kStages) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&acc_full[buf]);
+        if (leader) umma_commit(&acc_full[buf]);
         buf ^= 1;
       }
     }
@@ -346,7 +350,8 @@ __global__ void __launch_bounds__(kThreads, 1) pw_wgrad_kernel(const __grid_cons
   const int rows = p.bw * p.bh;
 
   if (warp == 4) {
-    if (lane == 0) {
+    const bool leader = elect_one() != 0;
+    {
       int s = 0;
       uint32_t ph = 0;
       const uint32_t bytes = 4 * rows * COB * 2 + rows * CIB * 2;
@@ -357,13 +362,15 @@ __global__ void __launch_bounds__(kThreads, 1) pw_wgrad_kernel(const __grid_cons
         const int dd = static_cast<int>(r % p.d);
         const int n = static_cast<int>(r / p.d);
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], bytes);
         uint8_t* st = smem + s * C::Stage;
+        if (leader) {
+          mbar_expect_tx(&full[s], bytes);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tma_load_5d(st + q * 8192, &maps.dy[q], &full[s], cob * COB, w0, h0, dd, n);
+          for (int q = 0; q < 4; ++q) tma_load_5d(st + q * 8192, &maps.dy[q], &full[s], cob * COB, w0, h0, dd, n);
 #pragma unroll
-        for (int u = 0; u < C::NSUB; ++u)
-          tma_load_5d(st + 4 * 8192 + u * C::XSub, &maps.x, &full[s], cib * CIB + u * 64, w0, h0, dd, n);
+          for (int u = 0; u < C::NSUB; ++u)
+            tma_load_5d(st + 4 * 8192 + u * C::XSub, &maps.x, &full[s], cib * CIB + u * 64, w0, h0, dd, n);
+        }
         if (++s == C::Stages) {
           s = 0;
           ph ^= 1;
@@ -371,7 +378,8 @@ __global__ void __launch_bounds__(kThreads, 1) pw_wgrad_kernel(const __grid_cons
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    const bool leader = elect_one() != 0;
+    {
       constexpr uint32_t kSwzA = (COB == 64) ? kSwizzle128 : kSwizzle64;
       constexpr uint32_t kSboA = (COB == 64) ? 1024 : 512;
       const uint64_t adesc_hi = make_smem_desc_hi(8192, kSboA, kSwzA);
@@ -387,18 +395,19 @@ __global__ void __launch_bounds__(kThreads, 1) pw_wgrad_kernel(const __grid_cons
 #pragma unroll
         for (int i = 0; i < C::NMMA; ++i) {
           for (int ks = 0; ks < ksteps; ++ks) {
-            umma_bf16(tmem_base + i * CIB, smem_desc(adesc_hi, base + i * C::SP * 8192 + ks * 2 * kSboA),
-                      smem_desc(bdesc_hi, base + 4 * 8192 + ks * 2048), idesc, (first && ks == 0) ? 0u : 1u);
+            if (leader)
+              umma_bf16(tmem_base + i * CIB, smem_desc(adesc_hi, base + i * C::SP * 8192 + ks * 2 * kSboA),
+                        smem_desc(bdesc_hi, base + 4 * 8192 + ks * 2048), idesc, (first && ks == 0) ? 0u : 1u);
           }
         }
         first = 0;
-        umma_commit(&empty[s]);
+        if (leader) umma_commit(&empty[s]);
         if (++s == C::Stages) {
           s = 0;
           ph ^= 1;
         }
       }
-      umma_commit(acc_full);
+      if (leader) umma_commit(acc_full);
     }
   } else {
     mbar_wait(acc_full, 0);
