@@ -33,10 +33,11 @@ struct GateArgs {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
 // Sum each of part[0..d) over the block; afterwards every thread holds the totals.
-__device__ __forceinline__ void block_sum_vec(float (&part)[kMaxD], int d, float* red /* [kT/32][kMaxD] */) {
+template <int MD>
+__device__ __forceinline__ void block_sum_vec(float (&part)[MD], int d, float* red /* [kT/32][kMaxD] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < kMaxD; ++i) {
+  for (int i = 0; i < MD; ++i) {
     if (i < d) {
       float v = part[i];
 #pragma unroll
@@ -46,7 +47,7 @@ __device__ __forceinline__ void block_sum_vec(float (&part)[kMaxD], int d, float
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kMaxD; ++i) {
+  for (int i = 0; i < MD; ++i) {
     if (i < d) {
       float v = 0.f;
 #pragma unroll
@@ -91,15 +92,24 @@ __host__ __device__ inline size_t gate_smem_bytes(int c, int d) {
 }
 
 // Forward gates of sample n: fills sm.Se, s1, w1, w2, t, hdn, w3.
+// MD = compile-time bound on the number of energy bins (8 or 16): every per-bin vector lives in
+// registers with static indexing, so the unrolled code size grows with MD (quadratically in the
+// circular convolutions) - with MD = 16 the backward kernel was 19k instructions and spent its time
+// in instruction fetch.
+// DX > 0: the number of bins is the compile-time constant DX (= MD): guards fold away and the
+// circular index arithmetic `% d` becomes a constant modulo. The SPCCT data has 5 bins
+// (config.py:22), which gets its own instantiation.
+template <int MD, int DX>
 __device__ void gate_forward(const GateArgs& a, int n, GateSmem& sm) {
-  const int tid = threadIdx.x, c = a.c, d = a.d;
+  const int tid = threadIdx.x, c = a.c, d = DX > 0 ? DX : a.d;
   const float* S = a.S + static_cast<size_t>(n) * d * c;
-  float part[kMaxD];
+  float part[MD];
 #pragma unroll
-  for (int i = 0; i < kMaxD; ++i) part[i] = 0.f;
+  for (int i = 0; i < MD; ++i) part[i] = 0.f;
 #pragma unroll
-  for (int dd = 0; dd < kMaxD; ++dd) {
+  for (int dd = 0; dd < MD; ++dd) {
     if (dd < d) {
+      #pragma unroll 1
       for (int ch = tid; ch < c; ch += kT) {
         float se = a.flags ? S[dd * c + ch] : 0.f;
         if (a.flags & SPFF_GATE_EFILM) se = fmaf(se, a.g1[ch * d + dd], a.bt[ch * d + dd] * a.hw);
@@ -112,7 +122,7 @@ __device__ void gate_forward(const GateArgs& a, int n, GateSmem& sm) {
   const float inv_chw = 1.f / (static_cast<float>(c) * a.hw);
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < kMaxD; ++i)
+    for (int i = 0; i < MD; ++i)
       if (i < d) sm.s1[i] = part[i] * inv_chw;
   }
   __syncthreads();
@@ -131,6 +141,7 @@ __device__ void gate_forward(const GateArgs& a, int n, GateSmem& sm) {
   __syncthreads();
   if (a.flags & SPFF_GATE_CHANSE) {
     const float inv_dhw = 1.f / (static_cast<float>(d) * a.hw);
+    #pragma unroll 1
     for (int ch = tid; ch < c; ch += kT) {
       float s = 0.f;
       for (int dd = 0; dd < d; ++dd) s = fmaf(sm.Se[dd * c + ch], sm.w1[dd] * sm.w2[dd], s);
@@ -138,31 +149,38 @@ __device__ void gate_forward(const GateArgs& a, int n, GateSmem& sm) {
     }
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
+    #pragma unroll 1
     for (int j = warp; j < a.hid; j += kT / 32) {
       float s = 0.f;
+      #pragma unroll 1
       for (int ch = lane; ch < c; ch += 32) s = fmaf(a.w1[j * c + ch], sm.t[ch], s);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) sm.hdn[j] = fmaxf(s + a.b1[j], 0.f);
     }
     __syncthreads();
+    #pragma unroll 1
     for (int ch = tid; ch < c; ch += kT) {
       float v = a.b2[ch];
+      #pragma unroll 1
       for (int j = 0; j < a.hid; ++j) v = fmaf(a.w2[ch * a.hid + j], sm.hdn[j], v);
       sm.w3[ch] = sigmoidf_(v);
     }
   } else {
+    #pragma unroll 1
     for (int ch = tid; ch < c; ch += kT) sm.w3[ch] = 1.f;
   }
   __syncthreads();
 }
 
+template <int MD, int DX>
 __global__ void __launch_bounds__(kT) gate_fwd_kernel(GateArgs a, float* __restrict__ P, float* __restrict__ Q) {
   extern __shared__ float smem_f[];
   GateSmem sm = carve(smem_f, a.c, a.d);
   const int n = blockIdx.x;
-  gate_forward(a, n, sm);
-  const int c = a.c, d = a.d;
+  gate_forward<MD, DX>(a, n, sm);
+  const int c = a.c, d = DX > 0 ? DX : a.d;
+  #pragma unroll 1
   for (int idx = threadIdx.x; idx < d * c; idx += kT) {
     const int dd = idx / c, ch = idx % c;
     const float G = sm.w1[dd] * sm.w2[dd] * sm.w3[ch];
@@ -183,13 +201,14 @@ struct GateBwdOut {
   float* dw1; float* db1; float* dw2; float* db2;  // SE fc (+=)
 };
 
+template <int MD, int DX>
 __global__ void __launch_bounds__(kT)
 gate_bwd_kernel(GateArgs a, const float* __restrict__ R, const float* __restrict__ coef,
                 const float* __restrict__ gamma, GateBwdOut o) {
   extern __shared__ float smem_f[];
   GateSmem sm = carve(smem_f, a.c, a.d);
-  const int n = blockIdx.x, tid = threadIdx.x, c = a.c, d = a.d;
-  gate_forward(a, n, sm);
+  const int n = blockIdx.x, tid = threadIdx.x, c = a.c, d = DX > 0 ? DX : a.d;
+  gate_forward<MD, DX>(a, n, sm);
   const float* S = a.S + static_cast<size_t>(n) * d * c;
   const float* Rn = R + static_cast<size_t>(n) * d * c * 6;
   const bool efilm = a.flags & SPFF_GATE_EFILM;
@@ -197,13 +216,14 @@ gate_bwd_kernel(GateArgs a, const float* __restrict__ R, const float* __restrict
   const float inv_dhw = 1.f / (static_cast<float>(d) * a.hw);
 
   // (a) dG = dP*g1 + dQ*bt ; direct table grads ; dw3[c] ; dw12[d]
-  float dw12[kMaxD];
+  float dw12[MD];
 #pragma unroll
-  for (int i = 0; i < kMaxD; ++i) dw12[i] = 0.f;
+  for (int i = 0; i < MD; ++i) dw12[i] = 0.f;
+  #pragma unroll 1
   for (int ch = tid; ch < c; ch += kT) {
     float dw3 = 0.f;
 #pragma unroll
-    for (int dd = 0; dd < kMaxD; ++dd) {
+    for (int dd = 0; dd < MD; ++dd) {
       if (dd < d) {
         const float dP = Rn[(dd * c + ch) * 6 + 0], dQ = Rn[(dd * c + ch) * 6 + 1];
         const float g1 = efilm ? a.g1[ch * d + dd] : 1.f;
@@ -225,8 +245,10 @@ gate_bwd_kernel(GateArgs a, const float* __restrict__ R, const float* __restrict
   // (b) channel SE backward -> dt[c] (kept in sm.dv after use of dv)
   if (a.flags & SPFF_GATE_CHANSE) {
     const int lane = tid & 31, warp = tid >> 5;
+    #pragma unroll 1
     for (int j = warp; j < a.hid; j += kT / 32) {
       float s = 0.f;
+      #pragma unroll 1
       for (int ch = lane; ch < c; ch += 32) s = fmaf(a.w2[ch * a.hid + j], sm.dv[ch], s);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -237,10 +259,12 @@ gate_bwd_kernel(GateArgs a, const float* __restrict__ R, const float* __restrict
       }
     }
     __syncthreads();
+    #pragma unroll 1
     for (int ch = tid; ch < c; ch += kT) {
       const float dv = sm.dv[ch];
       atomicAdd(o.db2 + ch, dv);
       float dt = 0.f;
+      #pragma unroll 1
       for (int j = 0; j < a.hid; ++j) {
         atomicAdd(o.dw2 + ch * a.hid + j, dv * sm.hdn[j]);
         atomicAdd(o.dw1 + j * c + ch, sm.dpre[j] * sm.t[ch]);
@@ -249,25 +273,27 @@ gate_bwd_kernel(GateArgs a, const float* __restrict__ R, const float* __restrict
       sm.dv[ch] = dt;  // reuse: dt[c]
     }
   } else {
+    #pragma unroll 1
     for (int ch = tid; ch < c; ch += kT) sm.dv[ch] = 0.f;
   }
   __syncthreads();
 
   // (c) dSg = dt/(D*hw);  dw2[d] = dw12*w1 + sum_c dSg*Sf
-  float acc[kMaxD];
+  float acc[MD];
 #pragma unroll
-  for (int i = 0; i < kMaxD; ++i) acc[i] = 0.f;
+  for (int i = 0; i < MD; ++i) acc[i] = 0.f;
+  #pragma unroll 1
   for (int ch = tid; ch < c; ch += kT) {
     const float dsg = sm.dv[ch] * inv_dhw;
 #pragma unroll
-    for (int dd = 0; dd < kMaxD; ++dd)
+    for (int dd = 0; dd < MD; ++dd)
       if (dd < d) acc[dd] = fmaf(dsg, sm.Se[dd * c + ch] * sm.w1[dd], acc[dd]);
   }
   block_sum_vec(acc, d, sm.red);
   // (d) ds2 -> uniform part of dSf ; (e) dw1[d] = dw12*w2 + sum_c dSf*Se
-  float ds2c[kMaxD];  // ds2[d] / (c*hw)
+  float ds2c[MD];  // ds2[d] / (c*hw)
 #pragma unroll
-  for (int i = 0; i < kMaxD; ++i) {
+  for (int i = 0; i < MD; ++i) {
     ds2c[i] = 0.f;
     if (i < d) {
       const float dw2 = dw12[i] * sm.w1[i] + acc[i];
@@ -276,19 +302,20 @@ gate_bwd_kernel(GateArgs a, const float* __restrict__ R, const float* __restrict
     }
   }
 #pragma unroll
-  for (int i = 0; i < kMaxD; ++i) acc[i] = 0.f;
+  for (int i = 0; i < MD; ++i) acc[i] = 0.f;
+  #pragma unroll 1
   for (int ch = tid; ch < c; ch += kT) {
     const float dsg = sm.dv[ch] * inv_dhw;
 #pragma unroll
-    for (int dd = 0; dd < kMaxD; ++dd)
+    for (int dd = 0; dd < MD; ++dd)
       if (dd < d) acc[dd] = fmaf(dsg * sm.w2[dd] + ds2c[dd], sm.Se[dd * c + ch], acc[dd]);
   }
   block_sum_vec(acc, d, sm.red);
   // (f) Fourier gate backward: du, ds1, dkfg
   // dw1[d] lives in registers (acc/dw12 are block-uniform): every thread computes the small vectors
-  float du[kMaxD], ds1c[kMaxD];
+  float du[MD], ds1c[MD];
 #pragma unroll
-  for (int i = 0; i < kMaxD; ++i) {
+  for (int i = 0; i < MD; ++i) {
     du[i] = 0.f;
     if (i < d) {
       const float dw1 = dw12[i] * sm.w2[i] + acc[i];
@@ -297,12 +324,12 @@ gate_bwd_kernel(GateArgs a, const float* __restrict__ R, const float* __restrict
     }
   }
 #pragma unroll
-  for (int e = 0; e < kMaxD; ++e) {
+  for (int e = 0; e < MD; ++e) {
     ds1c[e] = 0.f;
     if (e < d && (a.flags & SPFF_GATE_FOURIER)) {
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < kMaxD; ++i)
+      for (int i = 0; i < MD; ++i)
         if (i < d) s = fmaf(du[i], a.kfg[(i - e + d) % d], s);
       ds1c[e] = s * inv_chw;
     }
@@ -311,16 +338,17 @@ gate_bwd_kernel(GateArgs a, const float* __restrict__ R, const float* __restrict
     // dkfg[r] += sum_i du[i] * s1[(i - r) mod d],  r = tid
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxD; ++i)
+    for (int i = 0; i < MD; ++i)
       if (i < d) s = fmaf(du[i], sm.s1[(i - tid + d) % d], s);
     atomicAdd(o.dkfg + tid, s);
   }
   // (g,h,i,j) per element: dSe, table grads through S_e, dS; IN backward coefficients
+  #pragma unroll 1
   for (int ch = tid; ch < c; ch += kT) {
     const float dsg = sm.dv[ch] * inv_dhw;
     float sum_dz = 0.f, sum_dzx = 0.f;
 #pragma unroll
-    for (int dd = 0; dd < kMaxD; ++dd) {
+    for (int dd = 0; dd < MD; ++dd) {
       if (dd < d) {
         const float dSf = dsg * sm.w2[dd] + ds2c[dd];
         const float dSe = dSf * sm.w1[dd] + ds1c[dd];
@@ -414,10 +442,10 @@ int spff_gate_micro_fwd(const float* S, const float* g1, const float* bt, const 
   if (e) return e;
   SPFF_REQUIRE(S && P && Q, "gate_micro_fwd: null pointer");
   const size_t smem = spff::gate_smem_bytes(c, s.d);
+  auto kern = s.d == 5 ? spff::gate_fwd_kernel<5, 5> : (s.d <= 8 ? spff::gate_fwd_kernel<8, 0> : spff::gate_fwd_kernel<16, 0>);
   if (smem > 48 * 1024)
-    SPFF_CUDA(cudaFuncSetAttribute(spff::gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
-  spff::gate_fwd_kernel<<<s.n, spff::kT, smem, static_cast<cudaStream_t>(stream)>>>(a, P, Q);
+    SPFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<s.n, spff::kT, smem, static_cast<cudaStream_t>(stream)>>>(a, P, Q);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -445,10 +473,10 @@ int spff_gate_micro_bwd(const float* R, const float* S, const float* coef, const
   }
   spff::GateBwdOut o{bcoef, dSa, Pout, dgamma, dbeta, dg1, dbt, dkfg, dse_w1, dse_b1, dse_w2, dse_b2};
   const size_t smem = spff::gate_smem_bytes(c, s.d);
+  auto kern = s.d == 5 ? spff::gate_bwd_kernel<5, 5> : (s.d <= 8 ? spff::gate_bwd_kernel<8, 0> : spff::gate_bwd_kernel<16, 0>);
   if (smem > 48 * 1024)
-    SPFF_CUDA(cudaFuncSetAttribute(spff::gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
-  spff::gate_bwd_kernel<<<s.n, spff::kT, smem, static_cast<cudaStream_t>(stream)>>>(a, R, coef, gamma, o);
+    SPFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<s.n, spff::kT, smem, static_cast<cudaStream_t>(stream)>>>(a, R, coef, gamma, o);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }

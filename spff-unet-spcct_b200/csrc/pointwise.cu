@@ -118,32 +118,35 @@ stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_b
 }
 
 // stem weight gradient: partial[block][tap][co] = sum over the block's voxels of dy[pos][co]*x[pos+tap]
-// one thread = one strip x 4 channels; all 27 taps accumulate in registers.
-__global__ void __launch_bounds__(256)
+// one thread = one strip x 2 channels (54 accumulators: 2-3 resident blocks per SM); the 16 threads of
+// a strip read the same input window (broadcast loads).
+constexpr int kStemWgCh = 2;
+
+__global__ void __launch_bounds__(256, 3)
 stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long lddy, int cout,
                   spff_shape s, float* __restrict__ partial) {
   extern __shared__ float red[];  // [warps][27][cout]
-  const int c4 = cout / 4;        // channel quads per voxel (must divide 32)
+  const int cg = cout / kStemWgCh;  // channel groups per voxel (must divide 32)
   const int strips = (s.w + kStrip - 1) / kStrip;
-  const long long total = static_cast<long long>(s.n) * s.d * s.h * strips * c4;
-  float acc[27][4];
+  const long long total = static_cast<long long>(s.n) * s.d * s.h * strips * cg;
+  float acc[27][kStemWgCh];
 #pragma unroll
   for (int t = 0; t < 27; ++t)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[t][k] = 0.f;
+    for (int k = 0; k < kStemWgCh; ++k) acc[t][k] = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     int v, w0, hq, dq;
     long long rowbase;
-    stem_decode(i, c4, strips, s, v, w0, hq, dq, rowbase);
-    float g[kStrip][4];
+    stem_decode(i, cg, strips, s, v, w0, hq, dq, rowbase);
+    float g[kStrip][kStemWgCh];
 #pragma unroll
     for (int j = 0; j < kStrip; ++j) {
-      uint2 raw = make_uint2(0, 0);
-      if (w0 + j < s.w) raw = __ldg(reinterpret_cast<const uint2*>(dy + (rowbase + w0 + j) * lddy + v * 4));
-      const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-      const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-      g[j][0] = g01.x; g[j][1] = g01.y; g[j][2] = g23.x; g[j][3] = g23.y;
+      unsigned int raw = 0;
+      if (w0 + j < s.w) raw = __ldg(reinterpret_cast<const unsigned int*>(dy + (rowbase + w0 + j) * lddy + v * 2));
+      const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
+      g[j][0] = g01.x;
+      g[j][1] = g01.y;
     }
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd) {
@@ -157,20 +160,20 @@ stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__
 #pragma unroll
           for (int j = 0; j < kStrip; ++j)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[t][k] = fmaf(g[j][k], xw[j + kw], acc[t][k]);
+            for (int k = 0; k < kStemWgCh; ++k) acc[t][k] = fmaf(g[j][k], xw[j + kw], acc[t][k]);
         }
       }
     }
   }
-  // lanes with the same (lane % c4) own the same channels (blockDim and gridDim*blockDim are multiples of c4)
+  // lanes with the same (lane % cg) own the same channels (blockDim and gridDim*blockDim are multiples of cg)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
   for (int t = 0; t < 27; ++t)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kStemWgCh; ++k) {
       float v = acc[t][k];
-      for (int o = 16; o >= c4; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane < c4) red[(warp * 27 + t) * cout + lane * 4 + k] = v;
+      for (int o = 16; o >= cg; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane < cg) red[(warp * 27 + t) * cout + lane * kStemWgCh + k] = v;
     }
   __syncthreads();
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
@@ -619,7 +622,7 @@ int upload_head(const float* w, const float* b, int K, int cin, cudaStream_t st)
   return 0;
 }
 
-constexpr int kStemWgradBlocksPerSm = 2;
+constexpr int kStemWgradBlocksPerSm = 3;
 constexpr int kHeadBwdBlocksPerSm = 2;
 
 }  // namespace

@@ -31,7 +31,7 @@ except ImportError:  # not in this image: a minimal stand-in with the same metho
     from ._lightning import pl
 
 from spff_b200 import dp, ops
-from spff_b200.engine import LossTally, NetConfig, SpffEngine
+from spff_b200.engine import LossTally, NetConfig, SpffEngine, StagedBatch
 
 from .config import BEST_LR, IGNORE_INDEX, NUM_CLASSES, NUM_FRAMES
 from .helpers import (LOSS_REGISTRY, ce_plus_macro_dice_loss, metrics_from_confusion, per_class_metrics_2d,
@@ -39,7 +39,7 @@ from .helpers import (LOSS_REGISTRY, ce_plus_macro_dice_loss, metrics_from_confu
 
 LOG_PER_CLASS = os.getenv("LOG_PER_CLASS", "1") == "1"
 # samples per group of the engine's schedule (activations of one group live at a time in fit_step)
-SAMPLE_GROUP = int(os.getenv("SPFF_SAMPLE_GROUP", "32"))
+SAMPLE_GROUP = int(os.getenv("SPFF_SAMPLE_GROUP", "128"))
 
 
 def _pick_first_if_seq(x):
@@ -379,6 +379,7 @@ class BaseLitModel(pl.LightningModule):
         self.is_3d = bool(is_3d)
         self.save_hyperparameters({"num_classes": num_classes, "lr": float(lr), "is_3d": bool(is_3d), **kwargs})
         self._fused = None
+        self._copy_stream = None
 
     def _normalize_input(self, x):
         return _pick_first_if_seq(x)
@@ -453,10 +454,19 @@ class BaseLitModel(pl.LightningModule):
             imgs = imgs.unsqueeze(1)
         core.materialize(imgs.shape[2])
         dev = core._flat.device
-        imgs = imgs.to(dev, non_blocking=True)
-        lbls = lbls.to(dev, non_blocking=True)
         if lbls.dtype not in (torch.uint8, torch.int64):
             lbls = lbls.long()
+        group = sample_group or core.sample_group
+        staged = None
+        if not imgs.is_cuda and not lbls.is_cuda:
+            # host batch: stream it in group by group on a copy stream, overlapped with the kernels
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            staged = StagedBatch(imgs, lbls, dev, group, self._copy_stream)
+            imgs, lbls = staged.x, staged.labels
+        else:
+            imgs = imgs.to(dev, non_blocking=True)
+            lbls = lbls.to(dev, non_blocking=True)
         st = self._fused
         if st is None or st["flat"] is not core._flat:
             st = self._fused = dict(flat=core._flat, grad=torch.zeros_like(core._flat), m=torch.zeros_like(core._flat),
@@ -466,8 +476,8 @@ class BaseLitModel(pl.LightningModule):
         st["grad"].zero_()
         st["tally"].zero()
         with torch.no_grad():
-            core.engine.train_step(imgs, lbls, st["G"], st["tally"], group=sample_group or core.sample_group,
-                                   ignore_index=IGNORE_INDEX)
+            core.engine.train_step(imgs, lbls, st["G"], st["tally"], group=group, ignore_index=IGNORE_INDEX,
+                                   staged=staged)
             gscale = dp.allreduce_grads(st["grad"])
             if optimize:
                 st["step"] += 1

@@ -488,10 +488,12 @@ class SpffEngine:
         T.finish(G)
 
     def train_step(self, x: torch.Tensor, labels: torch.Tensor, G: Dict[str, torch.Tensor], tally: "LossTally",
-                   group: int = 32, ignore_index: int = 255):
+                   group: int = 32, ignore_index: int = 255, staged: Optional["StagedBatch"] = None):
         """Fused forward + CE/confusion + backward over the batch in sample groups. Accumulates the
         parameter gradients of the batch-mean CE (helpers.py:798-801; the Dice term of the loss has
-        no gradient, helpers.py:782-795) into G and the loss statistics into `tally`."""
+        no gradient, helpers.py:782-795) into G and the loss statistics into `tally`.
+        `staged`: the batch is still arriving from pinned host memory on a copy stream (StagedBatch);
+        each group's forward waits only for its own slice."""
         x = self._check_input(x)
         bsz, _, d, h, w = x.shape
         if labels.shape != (bsz, d, h, w):
@@ -499,17 +501,63 @@ class SpffEngine:
         labels = labels.contiguous()
         self.refresh_weights()
         T = GateTables(self.cfg, self.params(), d, need_grad=True)
-        n_valid = (labels != ignore_index).sum().reshape(1)     # the CE normaliser spans the whole batch
+        n_valid = None
         p = self.params()
         for lo, hi in self._groups(bsz, group):
+            if staged is not None:
+                staged.wait_images(hi)
             B = self.buffers(hi - lo, d, h, w, x.device, train=True)
             self.forward_group(B, T, x[lo:hi], head="none")
+            if n_valid is None:   # the CE normaliser spans the whole batch; first needed here
+                if staged is not None:
+                    staged.wait_labels()
+                n_valid = (labels != ignore_index).sum().reshape(1)
             # head + CE + confusion + their backward in one pass; the logits never reach memory
             ops.head_loss_fused(B.out["dec1"], p["out.weight"], p["out.bias"], labels[lo:hi], ignore_index, n_valid, None,
                                 tally.nll, tally.count, tally.confusion, B.gout[1],
                                 G["out.weight"].view(-1, self.cfg.base), G["out.bias"], 1.0)
             self.backward_group(B, T, G, None)
         T.finish(G)
+
+
+class StagedBatch:
+    """Host -> device staging of one batch on a dedicated copy stream: the first image group, then
+    the labels (needed early for N_valid), then the remaining image groups; the compute stream waits
+    per group, so the transfer of group g+1 overlaps the kernels of group g. Host tensors should be
+    pinned (a pageable source still works, synchronously)."""
+
+    def __init__(self, imgs: torch.Tensor, labels: torch.Tensor, device, group: int, stream: torch.cuda.Stream):
+        bsz = imgs.shape[0]
+        self.x = torch.empty(imgs.shape, dtype=torch.float32, device=device)
+        self.labels = torch.empty(labels.shape, dtype=labels.dtype, device=device)
+        self.h2d_bytes = imgs.numel() * 4 + labels.numel() * labels.element_size()
+        self._events = []       # (upper sample index, event)
+        stream.wait_stream(torch.cuda.current_stream(device))
+        src = imgs if imgs.dtype == torch.float32 else imgs.float()
+        with torch.cuda.stream(stream):
+            first = True
+            for lo in range(0, bsz, max(1, group)):
+                hi = min(bsz, lo + group)
+                self.x[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                self._events.append((hi, ev))
+                if first:
+                    self.labels.copy_(labels, non_blocking=True)
+                    self._labels_ev = torch.cuda.Event()
+                    self._labels_ev.record(stream)
+                    first = False
+        self.x.record_stream(stream)
+        self.labels.record_stream(stream)
+
+    def wait_labels(self):
+        torch.cuda.current_stream().wait_event(self._labels_ev)
+
+    def wait_images(self, upto: int):
+        for hi, ev in self._events:
+            if hi >= upto:
+                torch.cuda.current_stream().wait_event(ev)
+                return
 
 
 class LossTally:
