@@ -66,6 +66,13 @@ int spff_pack_conv3_weight(const float* w, void* w_fwd, void* w_dgrad, int cout,
 /* y[n,d,h,w,0:cout] = conv3d(x)[...]  (F.conv3d at models.py:616-618 via nn.Sequential :1459-1469) */
 int spff_conv3d_k3_fwd(const void* x, long long ldx, int cin, const void* w_fwd, void* y, long long ldy, int cout,
                        spff_shape s, void* stream);
+/* Forward + InstanceNorm statistics of the output in the same kernel: the epilogue writes, per work
+ * item, the {sum, sum of squares} of its fp32 output tile to stat_partial[n][slots][2][cout]
+ * (slots = spff_conv3d_k3_stat_slots(s)); spff_in_coeffs_from_partials reduces them in a fixed
+ * order. Replaces the separate spff_in_stats pass over y. */
+int spff_conv3d_k3_stat_slots(spff_shape s);
+int spff_conv3d_k3_fwd_stats(const void* x, long long ldx, int cin, const void* w_fwd, void* y, long long ldy, int cout,
+                             spff_shape s, float* stat_partial, void* stream);
 /* dx = input gradient of the same convolution (ATen convolution_backward, grad_input). */
 int spff_conv3d_k3_dgrad(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
                          int cin, spff_shape s, void* stream);
@@ -113,6 +120,9 @@ int spff_in_stats(const void* x, long long ldx, int c, spff_shape s, double* sta
  * (summed over n; models.py:170-171 / Cicek3DUNet :721). */
 int spff_in_coeffs(const double* stats, const float* gamma, const float* beta, float eps, int n, int c,
                    long long count, int batch_stats, float* coef, void* stream);
+/* Same coefficients from the partial statistics of spff_conv3d_k3_fwd_stats. */
+int spff_in_coeffs_from_partials(const float* partial, int slots, const float* gamma, const float* beta, float eps, int n,
+                                 int c, long long count, float* coef, void* stream);
 /* y = lrelu(x*A + B) (bf16 -> bf16). */
 int spff_norm_act_apply(const void* x, long long ldx, const float* coef, void* y, long long ldy, int c, spff_shape s,
                         float slope, void* stream);

@@ -43,6 +43,8 @@ struct FpropParams {
   long long items;
   __nv_bfloat16* y;
   long long ldy;
+  float* stat_partial;  // STATS: [n][qtiles*ngroups][2][cout] per-item {sum, sum of squares} of the outputs
+  int cout;
 };
 
 template <int KC, bool RES>
@@ -58,7 +60,9 @@ struct SmemLayout {
   static constexpr int kOffW = kOffA + kStages * kABytes;
   static constexpr int kOffX = kOffW + kWStages * kWBytes;          // epilogue exchange rows
   static constexpr int kXBytes = 2 * 4 * 2 * kCoBlk * 4;
-  static constexpr int kOffBar = kOffX + kXBytes;
+  static constexpr int kOffS = kOffX + kXBytes;                     // STATS: per-warp column sums [4][2][32]
+  static constexpr int kSBytes = 4 * 2 * kCoBlk * 4;
+  static constexpr int kOffBar = kOffS + kSBytes;
   static constexpr int kNumBars = 2 * kStages + 2 * 3 + 2 * kMaxPlanes;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kTotal = kOffTmem + 16;
@@ -68,7 +72,26 @@ struct SmemLayout {
 // group completes at the end of the item. Resident weights (RES = true): input plane -> kh; output
 // plane j is complete once input plane j+1 is consumed, so its epilogue overlaps the MMAs of the
 // following planes and of the next item (per-plane full/empty barriers on the TMEM accumulators).
-template <int KC, bool RES>
+// Sum the 32 per-lane values of each of 32 columns across the warp: afterwards a[0] of lane L holds
+// the total of column L (transpose-reduce: 31 shuffles instead of 32 x 5).
+__device__ __forceinline__ void warp_column_sums(float (&a)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool hi = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = hi ? a[i + half] : a[i];
+      const float send = hi ? a[i] : a[i + half];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+}
+
+// STATS: the epilogue also produces the InstanceNorm statistics of its output tile (sum and sum of
+// squares per output channel, fp32 values before the bf16 rounding) as one partial row per work
+// item - no atomics, reduced in a fixed order by spff_in_coeffs_from_partials. This removes the
+// separate statistics pass over the freshly written conv output.
+template <int KC, bool RES, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const FpropParams p) {
@@ -78,6 +101,7 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint8_t* sA = smem + L::kOffA;
   uint8_t* sW = smem + L::kOffW;
   float* sX = reinterpret_cast<float*>(smem + L::kOffX);
+  float* sS = reinterpret_cast<float*>(smem + L::kOffS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* full = bars;
   uint64_t* empty = bars + L::kStages;
@@ -321,6 +345,12 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       const bool row_out = (m >= p.halo) && (m < p.halo + p.mstep) && (q < p.hw);
       const bool has_left = wq != 0;
       const bool has_right = wq != p.w - 1;
+      float ssum[kCoBlk], ssq[kCoBlk];
+      if constexpr (STATS) {
+#pragma unroll
+        for (int c = 0; c < kCoBlk; ++c) ssum[c] = ssq[c] = 0.f;
+      }
+      const float rowmask = row_out ? 1.f : 0.f;
       for (int d = d0; d < dend; ++d) {
         const int j = d - d0;
         mbar_wait(&acc_full[j], (accpar >> j) & 1u);
@@ -368,6 +398,11 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             l = (lane == 0) ? lb[e] : l;
             r = (lane == 31) ? rb[e] : r;
             v[e] = __uint_as_float(t1[c]) + (has_left ? l : 0.f) + (has_right ? r : 0.f);
+            if constexpr (STATS) {
+              const float vm = v[e] * rowmask;
+              ssum[c] += vm;
+              ssq[c] = fmaf(vm, v[e], ssq[c]);
+            }
           }
           packed[2 * c4] = pack_bf16x2(v[0], v[1]);
           packed[2 * c4 + 1] = pack_bf16x2(v[2], v[3]);
@@ -381,6 +416,22 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         }
         xpar ^= 1;
       }
+      if constexpr (STATS) {
+        // item totals: columns across the 32 rows of each warp, then across the 4 warps through smem
+        warp_column_sums(ssum, lane);
+        warp_column_sums(ssq, lane);
+        sS[(warp * 2 + 0) * kCoBlk + lane] = ssum[0];
+        sS[(warp * 2 + 1) * kCoBlk + lane] = ssq[0];
+        named_bar_sync(2, 128);
+        if (threadIdx.x < 2 * kCoBlk) {
+          const int which = threadIdx.x / kCoBlk, col = threadIdx.x % kCoBlk;
+          const float t = sS[(0 * 2 + which) * kCoBlk + col] + sS[(1 * 2 + which) * kCoBlk + col] +
+                          sS[(2 * 2 + which) * kCoBlk + col] + sS[(3 * 2 + which) * kCoBlk + col];
+          const long long slot = static_cast<long long>(n) * (p.qtiles * p.ngroups) + qt * p.ngroups + pg;
+          p.stat_partial[(slot * 2 + which) * p.cout + cb * kCoBlk + col] = t;
+        }
+        named_bar_sync(2, 128);   // sS is reused by the next item
+      }
     }
   }
 
@@ -392,9 +443,9 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   }
 }
 
-template <int KC, bool RES>
+template <int KC, bool RES, bool STATS>
 int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y, long long ldy, int cout,
-                 spff_shape s, cudaStream_t stream) {
+                 spff_shape s, float* stat_partial, cudaStream_t stream) {
   using L = SmemLayout<KC, RES>;
   FpropParams p;
   p.n = s.n;
@@ -416,6 +467,8 @@ int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y
   p.items = static_cast<long long>(s.n) * p.qtiles * p.ngroups * p.ncb;
   p.y = static_cast<__nv_bfloat16*>(y);
   p.ldy = ldy;
+  p.stat_partial = stat_partial;
+  p.cout = cout;
 
   CUtensorMap tx, tw;
   {
@@ -437,7 +490,7 @@ int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SPFF_CUDA(cudaFuncSetAttribute(conv3_fprop_kernel<KC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPFF_CUDA(cudaFuncSetAttribute(conv3_fprop_kernel<KC, RES, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    L::kTotal + 1024));
     attr_set = true;
   }
@@ -451,7 +504,7 @@ int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y
   } else if (p.items < ctas) {
     ctas = static_cast<int>(p.items);
   }
-  conv3_fprop_kernel<KC, RES><<<ctas, kThreads, L::kTotal + 1024, stream>>>(tx, tw, p);
+  conv3_fprop_kernel<KC, RES, STATS><<<ctas, kThreads, L::kTotal + 1024, stream>>>(tx, tw, p);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -518,8 +571,17 @@ int spff_pack_conv3_weight(const float* w, void* w_fwd, void* w_dgrad, int cout,
   return 0;
 }
 
+// partial statistics slots per sample of the forward kernel for this shape: qtiles * plane groups
+static int conv3_stat_slots(spff_shape s) {
+  const int hw = s.h * s.w;
+  const int mstep = (spff::kTileM % s.w == 0) ? 128 : 126;
+  const int qtiles = (hw + mstep - 1) / mstep;
+  const int G = s.d < spff::kMaxPlanes ? s.d : spff::kMaxPlanes;
+  return qtiles * ((s.d + G - 1) / G);
+}
+
 static int conv3_common(const void* x, long long ldx, int cin, const void* wpk, void* y, long long ldy, int cout,
-                        spff_shape s, void* stream, const char* who) {
+                        spff_shape s, float* stat_partial, void* stream, const char* who) {
   int e = spff_device_check();
   if (e) return e;
   SPFF_REQUIRE(x && wpk && y, "%s: null pointer", who);
@@ -533,20 +595,35 @@ static int conv3_common(const void* x, long long ldx, int cin, const void* wpk, 
                "%s: pointers must be 16-byte aligned", who);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // cin <= 64: one K chunk per tap, all 27 taps of a 32-channel output block stay resident in smem
-  if (cin == 64) return spff::launch_fprop<64, true>(x, ldx, cin, wpk, y, ldy, cout, s, st);
-  if (cin == 32) return spff::launch_fprop<32, true>(x, ldx, cin, wpk, y, ldy, cout, s, st);
-  if (spff::conv3_kc(cin) == 64) return spff::launch_fprop<64, false>(x, ldx, cin, wpk, y, ldy, cout, s, st);
-  return spff::launch_fprop<32, false>(x, ldx, cin, wpk, y, ldy, cout, s, st);
+  if (stat_partial) {
+    if (cin == 64) return spff::launch_fprop<64, true, true>(x, ldx, cin, wpk, y, ldy, cout, s, stat_partial, st);
+    if (cin == 32) return spff::launch_fprop<32, true, true>(x, ldx, cin, wpk, y, ldy, cout, s, stat_partial, st);
+    if (spff::conv3_kc(cin) == 64)
+      return spff::launch_fprop<64, false, true>(x, ldx, cin, wpk, y, ldy, cout, s, stat_partial, st);
+    return spff::launch_fprop<32, false, true>(x, ldx, cin, wpk, y, ldy, cout, s, stat_partial, st);
+  }
+  if (cin == 64) return spff::launch_fprop<64, true, false>(x, ldx, cin, wpk, y, ldy, cout, s, nullptr, st);
+  if (cin == 32) return spff::launch_fprop<32, true, false>(x, ldx, cin, wpk, y, ldy, cout, s, nullptr, st);
+  if (spff::conv3_kc(cin) == 64) return spff::launch_fprop<64, false, false>(x, ldx, cin, wpk, y, ldy, cout, s, nullptr, st);
+  return spff::launch_fprop<32, false, false>(x, ldx, cin, wpk, y, ldy, cout, s, nullptr, st);
 }
 
 int spff_conv3d_k3_fwd(const void* x, long long ldx, int cin, const void* w_fwd, void* y, long long ldy, int cout,
                        spff_shape s, void* stream) {
-  return conv3_common(x, ldx, cin, w_fwd, y, ldy, cout, s, stream, "conv3d_k3_fwd");
+  return conv3_common(x, ldx, cin, w_fwd, y, ldy, cout, s, nullptr, stream, "conv3d_k3_fwd");
+}
+
+int spff_conv3d_k3_stat_slots(spff_shape s) { return conv3_stat_slots(s); }
+
+int spff_conv3d_k3_fwd_stats(const void* x, long long ldx, int cin, const void* w_fwd, void* y, long long ldy, int cout,
+                             spff_shape s, float* stat_partial, void* stream) {
+  SPFF_REQUIRE(stat_partial, "conv3d_k3_fwd_stats: null partial buffer");
+  return conv3_common(x, ldx, cin, w_fwd, y, ldy, cout, s, stat_partial, stream, "conv3d_k3_fwd_stats");
 }
 
 int spff_conv3d_k3_dgrad(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
                          int cin, spff_shape s, void* stream) {
-  return conv3_common(dy, lddy, cout, w_dgrad, dx, lddx, cin, s, stream, "conv3d_k3_dgrad");
+  return conv3_common(dy, lddy, cout, w_dgrad, dx, lddx, cin, s, nullptr, stream, "conv3d_k3_dgrad");
 }
 
 }  // extern "C"

@@ -185,6 +185,33 @@ __global__ void in_coeffs_kernel(const double* __restrict__ stats, const float* 
   reinterpret_cast<float4*>(coef)[i] = o;
 }
 
+// coef from the per-item partial statistics the conv epilogue wrote: partial[n][slots][2][c].
+// Fixed summation order (double) -> bit-reproducible coefficients.
+__global__ void in_coeffs_partial_kernel(const float* __restrict__ partial, int slots, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float eps, int n, int c, double count,
+                                         float* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int s = i / c, ch = i % c;
+  const float* base = partial + static_cast<size_t>(s) * slots * 2 * c + ch;
+  double sum = 0, sq = 0;
+  for (int k = 0; k < slots; ++k) {
+    sum += base[static_cast<size_t>(k) * 2 * c];
+    sq += base[static_cast<size_t>(k) * 2 * c + c];
+  }
+  const double mean = sum / count;
+  double var = sq / count - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float A = rstd * (gamma ? gamma[ch] : 1.f);
+  float4 o;
+  o.x = A;
+  o.y = (beta ? beta[ch] : 0.f) - static_cast<float>(mean) * A;
+  o.z = static_cast<float>(mean);
+  o.w = rstd;
+  reinterpret_cast<float4*>(coef)[i] = o;
+}
+
 __device__ __forceinline__ void load_ab(const float* __restrict__ coef, int n, int c, int v, float (&A)[8],
                                         float (&B)[8]) {
   const float4* cf = reinterpret_cast<const float4*>(coef) + static_cast<long long>(n) * c + v * 8;
@@ -786,6 +813,17 @@ int spff_in_coeffs(const double* stats, const float* gamma, const float* beta, f
   const int total = n * c;
   spff::in_coeffs_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       stats, gamma, beta, eps, n, c, static_cast<double>(count), batch_stats, coef);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_in_coeffs_from_partials(const float* partial, int slots, const float* gamma, const float* beta, float eps, int n,
+                                 int c, long long count, float* coef, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(partial && coef && slots > 0 && n > 0 && c > 0, "in_coeffs_from_partials: bad arguments");
+  const int total = n * c;
+  spff::in_coeffs_partial_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      partial, slots, gamma, beta, eps, n, c, static_cast<double>(count), coef);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -42,6 +42,8 @@ _PROTOTYPES = {
     "spff_debug_set": [c_int, _LL],
     "spff_pack_conv3_weight": [_P, _P, _P, c_int, c_int, _P],
     "spff_conv3d_k3_fwd": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P],
+    "spff_conv3d_k3_stat_slots": [Shape],
+    "spff_conv3d_k3_fwd_stats": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P, _P],
     "spff_conv3d_k3_dgrad": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P],
     "spff_conv3d_k3_wgrad_workspace": [c_int, c_int, Shape],
     "spff_conv3d_k3_wgrad": [_P, _LL, c_int, _P, _LL, c_int, Shape, _P, c_float, _P, c_size_t, _P],
@@ -55,6 +57,7 @@ _PROTOTYPES = {
     "spff_convt_k122_wgrad": [_P, _LL, c_int, _P, _LL, c_int, Shape, _P, c_float, _P, c_size_t, _P],
     "spff_in_stats": [_P, _LL, c_int, Shape, _P, _P],
     "spff_in_coeffs": [_P, _P, _P, c_float, c_int, c_int, _LL, c_int, _P, _P],
+    "spff_in_coeffs_from_partials": [_P, c_int, _P, _P, c_float, c_int, c_int, _LL, _P, _P],
     "spff_norm_act_apply": [_P, _LL, _P, _P, _LL, c_int, Shape, c_float, _P],
     "spff_norm_act_reduce": [_P, _LL, _P, _P, c_int, Shape, c_float, _P],
     "spff_norm_act_affine_apply": [_P, _LL, _P, _P, _P, _P, _LL, _P, _LL, c_int, Shape, c_float, _P],

@@ -117,6 +117,8 @@ class _GroupBuffers:
         self.cat = {l: bf(*self.HW[l], 2 * self.C[l]) for l in (1, 2, 3)}
         self.pool = {l: bf(*self.HW[l + 1], self.C[l]) for l in (1, 2, 3)}    # pooled output of level l
         self.x1, self.a1, self.x2, self.out = {}, {}, {}, {}
+        self.partial: Dict[str, torch.Tensor] = {}
+        self.slots: Dict[str, int] = {}
         self.f64 = _Pool(torch.float64, device)
         self.f32 = _Pool(torch.float32, device)
         self.idx: Dict[str, int] = {}
@@ -131,6 +133,11 @@ class _GroupBuffers:
             for j in (1, 2):
                 self.idx[f"{b}.stats{j}"] = self.f64.reserve(n, c, 2)
             self.idx[f"{b}.S"] = self.f32.reserve(n, d, c)
+            # per-item partial statistics written by the conv epilogue (no zeroing needed)
+            self.slots[b] = ops.conv3d_k3_stat_slots(Shape(n, d, hh, ww))
+            for j in (1, 2):
+                if not (b == "enc1" and j == 1):
+                    self.partial[f"{b}.{j}"] = torch.empty(n, self.slots[b], 2, c, device=device)
         self.f64.commit()
         self.f32.commit()
         self.coef = {f"{b}.{j}": torch.empty(n, self.C[_LEVEL[b]], 4, device=device) for b in BLOCKS for j in (1, 2)}
@@ -308,19 +315,21 @@ class SpffEngine:
         shp = B.shape(l)
         count = B.d * shp.h * shp.w
         # conv1 -> IN statistics -> a1 = lrelu(IN(x1))
+        # (the tensor-core convs produce the InstanceNorm statistics in their epilogue; the stem needs a pass)
         if b == "enc1":
             ops.conv3d_stem_fwd(B.x_in, p[f"{b}.{cn1}.0.weight"], B.x1[b], c)
+            st1 = B.f64.get(B.idx[f"{b}.stats1"])
+            ops.in_stats(B.x1[b], c, st1)
+            ops.in_coeffs(st1, p[f"{b}.{cn1}.1.weight"], p[f"{b}.{cn1}.1.bias"], EPS, B.n, c, count, B.coef[f"{b}.1"])
         else:
-            ops.conv3d_k3_fwd(xin, cin, self._packed[f"{b}.1"][0], B.x1[b], c)
-        st1 = B.f64.get(B.idx[f"{b}.stats1"])
-        ops.in_stats(B.x1[b], c, st1)
-        ops.in_coeffs(st1, p[f"{b}.{cn1}.1.weight"], p[f"{b}.{cn1}.1.bias"], EPS, B.n, c, count, B.coef[f"{b}.1"])
+            ops.conv3d_k3_fwd_stats(xin, cin, self._packed[f"{b}.1"][0], B.x1[b], c, B.partial[f"{b}.1"])
+            ops.in_coeffs_from_partials(B.partial[f"{b}.1"], B.slots[b], p[f"{b}.{cn1}.1.weight"], p[f"{b}.{cn1}.1.bias"],
+                                        EPS, B.n, c, count, B.coef[f"{b}.1"])
         ops.norm_act_apply(B.x1[b], B.coef[f"{b}.1"], B.a1[b], c, SLOPE)
         # conv2 -> IN statistics -> (S -> P,Q) -> out = lrelu(IN(x2))*P + Q (+ pooled copy)
-        ops.conv3d_k3_fwd(B.a1[b], c, self._packed[f"{b}.2"][0], B.x2[b], c)
-        st2 = B.f64.get(B.idx[f"{b}.stats2"])
-        ops.in_stats(B.x2[b], c, st2)
-        ops.in_coeffs(st2, p[f"{b}.{cn2}.1.weight"], p[f"{b}.{cn2}.1.bias"], EPS, B.n, c, count, B.coef[f"{b}.2"])
+        ops.conv3d_k3_fwd_stats(B.a1[b], c, self._packed[f"{b}.2"][0], B.x2[b], c, B.partial[f"{b}.2"])
+        ops.in_coeffs_from_partials(B.partial[f"{b}.2"], B.slots[b], p[f"{b}.{cn2}.1.weight"], p[f"{b}.{cn2}.1.bias"],
+                                    EPS, B.n, c, count, B.coef[f"{b}.2"])
         flags = cfg.block_flags(b)
         P = Q = None
         if flags:

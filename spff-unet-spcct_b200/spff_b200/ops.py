@@ -53,6 +53,26 @@ def conv3d_k3_fwd(x, cin, w_fwd, y, cout):
     call("spff_conv3d_k3_fwd", ptr(x), ldx, cin, ptr(w_fwd), ptr(y), ldy, cout, s, stream_ptr())
 
 
+def conv3d_k3_stat_slots(shape: Shape) -> int:
+    return int(_lib.lib.spff_conv3d_k3_stat_slots(shape))
+
+
+def conv3d_k3_fwd_stats(x, cin, w_fwd, y, cout, partial):
+    """Forward conv + per-item InstanceNorm partial statistics of y (fp32 [n, slots, 2, cout])."""
+    s, ldx = _view(x, cin)
+    s2, ldy = _view(y, cout)
+    assert (s.n, s.d, s.h, s.w) == (s2.n, s2.d, s2.h, s2.w)
+    assert partial.dtype == torch.float32 and partial.is_contiguous()
+    assert partial.numel() >= s.n * conv3d_k3_stat_slots(s) * 2 * cout
+    _lib.NOTE = conv3_flops(s, cin, cout)
+    call("spff_conv3d_k3_fwd_stats", ptr(x), ldx, cin, ptr(w_fwd), ptr(y), ldy, cout, s, ptr(partial), stream_ptr())
+
+
+def in_coeffs_from_partials(partial, slots, gamma, beta, eps, n, c, count, coef):
+    call("spff_in_coeffs_from_partials", ptr(partial), int(slots), ptr(gamma), ptr(beta), float(eps), n, c, int(count),
+         ptr(coef), stream_ptr())
+
+
 def conv3d_k3_dgrad(dy, cout, w_dgrad, dx, cin):
     s, lddy = _view(dy, cout)
     s2, lddx = _view(dx, cin)

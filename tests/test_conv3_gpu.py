@@ -133,3 +133,45 @@ def test_conv3_wgrad(n, d, h, w, cin, cout):
     ops.conv3d_k3_wgrad(xb, cin, dyb, cout, dw, 1.0)
     torch.cuda.synchronize()
     assert ((dw - 2 * ref).norm() / ref.norm()) < 2e-4
+
+
+@pytest.mark.parametrize("n,d,h,w,cin,cout", CASES)
+def test_conv3_fwd_with_fused_statistics(n, d, h, w, cin, cout):
+    """spff_conv3d_k3_fwd_stats: same output as the plain forward (bit-exact) and InstanceNorm
+    coefficients from its per-item partial statistics == those of the separate statistics pass
+    (mean to 1e-4 abs of a unit-scale tensor, rstd to 1e-3 rel: the fused statistics see the fp32
+    values before the bf16 rounding)."""
+    from spff_b200 import ops
+    from spff_b200._lib import Shape
+
+    x = _to_ndhwc_bf16(_mk(n, cin, d, h, w, 11))
+    wt = _mk(cout, cin, 3, 3, 3, 12) * (1.0 / (27 * cin) ** 0.5)
+    wf, _ = ops.pack_conv3_weight(wt)
+    y0 = torch.empty(n, d, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    ops.conv3d_k3_fwd(x, cin, wf, y0, cout)
+    slots = ops.conv3d_k3_stat_slots(Shape(n, d, h, w))
+    partial = torch.full((n, slots, 2, cout), float("nan"), device="cuda")
+    y1 = torch.full_like(y0, float("nan"))
+    ops.conv3d_k3_fwd_stats(x, cin, wf, y1, cout, partial)
+    assert torch.equal(y0, y1)
+    assert not torch.isnan(partial).any()
+    gamma = torch.rand(cout, device="cuda") + 0.5
+    beta = torch.randn(cout, device="cuda")
+    coef_p = torch.empty(n, cout, 4, device="cuda")
+    ops.in_coeffs_from_partials(partial, slots, gamma, beta, 1e-5, n, cout, d * h * w, coef_p)
+    stats = torch.zeros(n, cout, 2, dtype=torch.float64, device="cuda")
+    ops.in_stats(y0, cout, stats)
+    coef_s = torch.empty(n, cout, 4, device="cuda")
+    ops.in_coeffs(stats, gamma, beta, 1e-5, n, cout, d * h * w, coef_s)
+    # the separate pass sees bf16-rounded values: per-element error <= 2^-9 |y|, so the means may differ by
+    # ~2^-9 * max|y| / sqrt(count) (6 sigma allowed), the second moments by ~2^-8 relative / sqrt(count)
+    count = d * h * w
+    atol_mean = 6 * 2.0 ** -9 * float(y0.float().abs().max()) / count ** 0.5 + 1e-6
+    rtol_rstd = 6 * 2.0 ** -8 / count ** 0.5 + 1e-4
+    assert torch.allclose(coef_p[..., 2], coef_s[..., 2], atol=atol_mean)            # mean
+    assert torch.allclose(coef_p[..., 3], coef_s[..., 3], rtol=rtol_rstd)            # rstd
+    assert torch.allclose(coef_p[..., 0], coef_s[..., 0], rtol=rtol_rstd)            # A = rstd*gamma
+    # against fp64 statistics of the exact convolution
+    ref = F.conv3d(_from_ndhwc(x, cin).double(), wt.to(torch.bfloat16).double(), padding=1)
+    assert torch.allclose(coef_p[..., 2].double(), ref.mean(dim=(2, 3, 4)), atol=1e-5)
+    assert torch.allclose(coef_p[..., 3].double(), 1.0 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5), rtol=1e-4)
