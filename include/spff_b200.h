@@ -60,8 +60,9 @@ int spff_debug_set(int key, long long value);
  * cin, cout multiples of 32 (the Cin = 1 stem has its own entry points below). */
 /* Elements of one packed weight operand: 27*cin*cout bf16. */
 /* nn.Conv3d weight [cout][cin][3][3][3] fp32 -> bf16 GEMM operands (either may be NULL):
- *   w_fwd   [cout/32][kh][cin/KC][kd][kw][32][KC]          KC = 64 if cin % 64 == 0 else 32
- *   w_dgrad [cin/32][kh][cout/KC'][kd][kw][32][KC']        taps flipped, in/out transposed */
+ *   w_fwd   [cout/32][kh][cin/KC][2-kd][kw][32][KC]        KC = 64 if cin % 64 == 0 else 32
+ *   w_dgrad [cin/32][kh][cout/KC'][2-kd][kw][32][KC']      taps flipped, in/out transposed
+ * (opaque to callers: only spff_conv3d_k3_fwd/_fwd_stats/_dgrad consume them). */
 int spff_pack_conv3_weight(const float* w, void* w_fwd, void* w_dgrad, int cout, int cin, void* stream);
 /* y[n,d,h,w,0:cout] = conv3d(x)[...]  (F.conv3d at models.py:616-618 via nn.Sequential :1459-1469) */
 int spff_conv3d_k3_fwd(const void* x, long long ldx, int cin, const void* w_fwd, void* y, long long ldy, int cout,

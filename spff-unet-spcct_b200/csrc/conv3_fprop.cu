@@ -255,26 +255,37 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       // shared window is < 256 KB, so the field never overflows into its neighbours
       const uint64_t a_desc0 = smem_desc(desc_hi, smem_u32(sA));
       const uint64_t w_desc0 = smem_desc(desc_hi, smem_u32(sW));
+      // One A stage (input plane dp, one kh) feeds the output planes dp-1, dp, dp+1 of the group through
+      // the taps kd = 2, 1, 0. The kd blocks of the packed weights are stored in DESCENDING kd, i.e. in
+      // ascending output plane, and plane j's accumulator sits at TMEM column j*96: two neighbouring
+      // output planes are therefore ONE MMA with N = 192 (the A tile is read from shared memory once
+      // for both), as long as their accumulate flags agree. Returns the updated touched mask.
+      const uint32_t idesc2 = make_idesc_bf16(kTileM, 2 * kN, 0, 0);
       auto stage_mmas = [&](uint64_t adesc, uint64_t wdesc, int dp, int d0, int dend, uint32_t touched) -> uint32_t {
-#pragma unroll
-        for (int kd = 0; kd < 3; ++kd) {
-          const int dout = dp - (kd - 1);
-          if (dout >= d0 && dout < dend) {
-            const int j = dout - d0;
-            if (!((touched >> j) & 1u)) {  // first MMA into this accumulator: the epilogue must have drained it
-              mbar_wait(&acc_empty[j], ((accpar >> j) & 1u) ^ 1u);
-              accpar ^= 1u << j;
-              tc_fence_after();
+        const int jlo = max(dp - 1, d0) - d0, jhi = min(dp + 1, dend - 1) - d0;
+        int j = jlo;
+        while (j <= jhi) {
+          const uint32_t tj = (touched >> j) & 1u;
+          const bool pair = (j + 1 <= jhi) && (((touched >> (j + 1)) & 1u) == tj);
+          const int cnt = pair ? 2 : 1;
+          if (!tj) {  // first MMA into these accumulators: the epilogue must have drained them
+            for (int q = j; q < j + cnt; ++q) {
+              mbar_wait(&acc_empty[q], ((accpar >> q) & 1u) ^ 1u);
+              accpar ^= 1u << q;
             }
-            const uint32_t dcol = tmem_base + j * kN;
-#pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              const uint64_t ad = adesc + static_cast<uint64_t>(k * 2);
-              const uint64_t bd = wdesc + static_cast<uint64_t>(kd * (L::kWBlock >> 4) + k * 2);
-              if (leader) umma_bf16(dcol, ad, bd, idesc, ((touched >> j) & 1u) | (k > 0 ? 1u : 0u));
-            }
-            touched |= 1u << j;
+            tc_fence_after();
           }
+          const uint32_t dcol = tmem_base + j * kN;
+          const int blk = j + d0 - dp + 1;   // weight block of the first plane of the run (= 2 - kd)
+          const uint64_t bd0 = wdesc + static_cast<uint64_t>(blk * (L::kWBlock >> 4));
+          const uint32_t id = pair ? idesc2 : idesc;
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            if (leader) umma_bf16(dcol, adesc + static_cast<uint64_t>(k * 2), bd0 + static_cast<uint64_t>(k * 2), id,
+                                  tj | (k > 0 ? 1u : 0u));
+          }
+          touched |= (pair ? 3u : 1u) << j;
+          j += cnt;
         }
         return touched;
       };
@@ -511,8 +522,9 @@ int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y
 
 // ---------------------------------------------------------------------------------------------
 // Weight packing: nn.Conv3d weight [Cout][Cin][3][3][3] fp32 -> bf16 GEMM operand
-//   P[cb][kh][kc][kd][kw][co32][KC],  value = w[cb*32+co][kc*KC+k][kd][kh][kw]          (forward)
-//   P[cb][kh][kc][kd][kw][ci32][KC],  value = w[kc*KC+k][cb*32+ci][2-kd][2-kh][2-kw]    (dgrad)
+//   P[cb][kh][kc][b][kw][co32][KC],  value = w[cb*32+co][kc*KC+k][2-b][kh][kw]          (forward)
+//   P[cb][kh][kc][b][kw][ci32][KC],  value = w[kc*KC+k][cb*32+ci][b][2-kh][2-kw]       (dgrad)
+// b = 2 - kd: blocks in descending tap order, so that block b serves output plane dp - 1 + b.
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_conv3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout,
                                          int cin, int KC, int dgrad) {
@@ -539,10 +551,11 @@ __global__ void pack_conv3_weight_kernel(const float* __restrict__ w, __nv_bfloa
     const int go = cb * kCoBlk + co;
     const int gi = kc * KC + k;
     float v;
+    const int kdt = 2 - kd;   // the kd blocks are stored in descending tap order (ascending output plane)
     if (!dgrad)
-      v = w[((static_cast<long long>(go) * cin + gi) * 3 + kd) * 9 + kh * 3 + kw];
+      v = w[((static_cast<long long>(go) * cin + gi) * 3 + kdt) * 9 + kh * 3 + kw];
     else
-      v = w[((static_cast<long long>(gi) * cin + go) * 3 + (2 - kd)) * 9 + (2 - kh) * 3 + (2 - kw)];
+      v = w[((static_cast<long long>(gi) * cin + go) * 3 + (2 - kdt)) * 9 + (2 - kh) * 3 + (2 - kw)];
     out[i] = __float2bfloat16(v);
   }
 }
