@@ -1,7 +1,7 @@
 // CUDA-core kernels of the hot path that are not GEMM-shaped enough for the tensor pipe:
 //   * the Cin = 1 stem convolution (enc1.pre.0 / enc1.b1.0, reference innovative3D/models.py:616-618
-//     with in_channels = 1, models.py:1551) — 27 taps x 32 outputs per voxel, forward and weight
-//     gradient (the network input needs no gradient);
+//     with in_channels = 1, models.py:1551) — 27 taps x 32 outputs per voxel: forward on the CUDA cores,
+//     weight gradient as a warp-level mma.sync GEMM (the network input needs no gradient);
 //   * the 1x1x1 classification head nn.Conv3d(32, num_classes, 1) (models.py:674) forward, arg-max
 //     and backward;
 //   * cross-entropy with ignore_index + the hard confusion tally that macro_dice_loss and
@@ -23,6 +23,9 @@ constexpr int kStemCo = 32;   // stem output channels
 __constant__ float c_head_w[kMaxK * kHeadC];
 __constant__ float c_head_b[kMaxK];
 
+__device__ __forceinline__ uint32_t smem_u32_local(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -117,70 +120,136 @@ stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_b
   }
 }
 
-// stem weight gradient: partial[block][tap][co] = sum over the block's voxels of dy[pos][co]*x[pos+tap]
-// one thread = one strip x 2 channels (54 accumulators: 2-3 resident blocks per SM); the 16 threads of
-// a strip read the same input window (broadcast loads).
-constexpr int kStemWgCh = 2;
+// ---------------------------------------------------------------------------------------------
+// Stem weight gradient on the tensor cores. dw[tap][co] = sum_pos x[pos + off(tap)] * dy[pos][co] is a
+// GEMM with M = 27 taps (padded to 32), N = 32 output channels, K = positions. The operands are far
+// too small for a tcgen05 tile pipeline (one 32 x 32 accumulator), so this uses warp-level
+// mma.sync m16n8k16 (bf16 in, fp32 accumulate): a warp owns one segment of <= 128 positions of an
+// image row at a time, stages the 9 x (128 + 2) input window (fp32 -> bf16) and 16-position dy tiles
+// in shared memory, builds the im2col A fragments straight from the window (tap = row/column offset)
+// and keeps the 32 x 32 accumulator in registers across all its segments.
+// x enters the product rounded to bf16 (the forward stem reads it in fp32): a 2^-9 relative,
+// zero-mean perturbation per element of a sum over ~10^8 positions.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSwgWarps = 8;
+constexpr int kSwgSeg = 128;                 // positions per segment
+constexpr int kSwgWin = kSwgSeg + 2 + 2;     // window columns (+2 halo, +2 so that 32-bit pair loads stay inside)
+constexpr int kSwgDyPitch = 40;              // bf16 per staged dy row (32 + 8 pad: conflict-free ldmatrix)
+constexpr int kSwgBlocksPerSm = 2;
 
-__global__ void __launch_bounds__(256, 3)
-stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long lddy, int cout,
-                  spff_shape s, float* __restrict__ partial) {
-  extern __shared__ float red[];  // [warps][27][cout]
-  const int cg = cout / kStemWgCh;  // channel groups per voxel (must divide 32)
-  const int strips = (s.w + kStrip - 1) / kStrip;
-  const long long total = static_cast<long long>(s.n) * s.d * s.h * strips * cg;
-  float acc[27][kStemWgCh];
+__global__ void __launch_bounds__(kSwgWarps * 32, kSwgBlocksPerSm)
+stem_wgrad_mma_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, long long lddy, spff_shape s,
+                      float* __restrict__ partial /* [block][27][32] */) {
+  __shared__ __align__(16) __nv_bfloat16 xs[kSwgWarps][9][kSwgWin];
+  __shared__ __align__(16) __nv_bfloat16 dys[kSwgWarps][16][kSwgDyPitch];
+  __shared__ float red[32 * 33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  float acc[2][4][4];
 #pragma unroll
-  for (int t = 0; t < 27; ++t)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int k = 0; k < kStemWgCh; ++k) acc[t][k] = 0.f;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    int v, w0, hq, dq;
-    long long rowbase;
-    stem_decode(i, cg, strips, s, v, w0, hq, dq, rowbase);
-    float g[kStrip][kStemWgCh];
+    for (int b = 0; b < 4; ++b)
 #pragma unroll
-    for (int j = 0; j < kStrip; ++j) {
-      unsigned int raw = 0;
-      if (w0 + j < s.w) raw = __ldg(reinterpret_cast<const unsigned int*>(dy + (rowbase + w0 + j) * lddy + v * 2));
-      const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
-      g[j][0] = g01.x;
-      g[j][1] = g01.y;
-    }
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  // the four im2col rows (taps) this thread feeds: g, g+8, g+16, g+24 -> element offset inside the window
+  int toff[4];
+  bool tok[4];
 #pragma unroll
-    for (int kd = 0; kd < 3; ++kd) {
+  for (int i = 0; i < 4; ++i) {
+    const int tap = g + 8 * i;
+    tok[i] = tap < 27;
+    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+    toff[i] = tok[i] ? (kd * 3 + kh) * kSwgWin + kw : 0;
+  }
+  const int segs = (s.w + kSwgSeg - 1) / kSwgSeg;
+  const long long nwork = static_cast<long long>(s.n) * s.d * s.h * segs;
+  const __nv_bfloat16* xw = &xs[warp][0][0];
+  const uint32_t* xw32 = reinterpret_cast<const uint32_t*>(xw);
+  for (long long work = static_cast<long long>(blockIdx.x) * kSwgWarps + warp; work < nwork;
+       work += static_cast<long long>(gridDim.x) * kSwgWarps) {
+    const int sg = static_cast<int>(work % segs);
+    const long long row = work / segs;                       // (n*d + dd)*h + hh
+    const int hh = static_cast<int>(row % s.h);
+    const int dd = static_cast<int>((row / s.h) % s.d);
+    const int w0 = sg * kSwgSeg;
+    const int wn = min(kSwgSeg, s.w - w0);                    // valid positions of this segment
+    const int wpad = (wn + 15) & ~15;
+    // input window: xs[kd*3+kh][c] = x[dd+kd-1][hh+kh-1][w0 + c - 1]
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        float xw[kStrip + 2];
-        stem_window(x, rowbase, w0, hq, dq, kd, kh, s, xw);
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int t = (kd * 3 + kh) * 3 + kw;
-#pragma unroll
-          for (int j = 0; j < kStrip; ++j)
-#pragma unroll
-            for (int k = 0; k < kStemWgCh; ++k) acc[t][k] = fmaf(g[j][k], xw[j + kw], acc[t][k]);
-        }
+    for (int r = 0; r < 9; ++r) {
+      const int d2 = dd + r / 3 - 1, h2 = hh + r % 3 - 1;
+      const bool rok = d2 >= 0 && d2 < s.d && h2 >= 0 && h2 < s.h;
+      const float* xr = x + (row + static_cast<long long>(r / 3 - 1) * s.h + (r % 3 - 1)) * s.w + w0 - 1;
+      for (int c = lane; c < wpad + 2; c += 32) {
+        const int w2 = w0 + c - 1;
+        const float v = (rok && w2 >= 0 && w2 < s.w) ? __ldg(xr + c) : 0.f;
+        xs[warp][r][c] = __float2bfloat16(v);
       }
     }
+    __syncwarp();
+    const __nv_bfloat16* dyrow = dy + (row * s.w + w0) * lddy;
+    for (int ks = 0; ks < wpad / 16; ++ks) {
+      {  // stage 16 positions x 32 channels of dy (zeros past the row end)
+        const int pos = lane >> 1, half = lane & 1;
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+        if (ks * 16 + pos < wn) {
+          const uint4* src = reinterpret_cast<const uint4*>(dyrow + static_cast<long long>(ks * 16 + pos) * lddy + half * 16);
+          v0 = __ldg(src);
+          v1 = __ldg(src + 1);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(&dys[warp][pos][half * 16]);
+        dst[0] = v0;
+        dst[1] = v1;
+      }
+      __syncwarp();
+      uint32_t bfr[4][2];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {  // one ldmatrix.x4.trans = B fragments of two 8-channel tiles
+        const int mi = lane >> 3, r = lane & 7;
+        const uint32_t addr = smem_u32_local(&dys[warp][r + 8 * (mi & 1)][8 * (2 * h2 + (mi >> 1))]);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(bfr[2 * h2][0]), "=r"(bfr[2 * h2][1]), "=r"(bfr[2 * h2 + 1][0]), "=r"(bfr[2 * h2 + 1][1])
+                     : "r"(addr));
+      }
+      uint32_t afr[2][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {       // row g + 8*i: m-tile i/2, fragment registers (i%2) and (i%2)+2
+#pragma unroll
+        for (int kh2 = 0; kh2 < 2; ++kh2) {
+          const int e = toff[i] + ks * 16 + 2 * t + 8 * kh2;   // element index of the pair (e, e+1)
+          const uint32_t lo = xw32[e >> 1], hi = xw32[(e >> 1) + 1];
+          const uint32_t v = __funnelshift_r(lo, hi, (e & 1) * 16);
+          afr[i >> 1][(i & 1) + 2 * kh2] = tok[i] ? v : 0u;
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+              : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+              : "r"(afr[mt][0]), "r"(afr[mt][1]), "r"(afr[mt][2]), "r"(afr[mt][3]), "r"(bfr[nt][0]), "r"(bfr[nt][1]));
+      __syncwarp();
+    }
   }
-  // lanes with the same (lane % cg) own the same channels (blockDim and gridDim*blockDim are multiples of cg)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // block reduction of the eight 32 x 32 accumulators (row = tap, column = channel)
+  for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
 #pragma unroll
-  for (int t = 0; t < 27; ++t)
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int k = 0; k < kStemWgCh; ++k) {
-      float v = acc[t][k];
-      for (int o = 16; o >= cg; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane < cg) red[(warp * 27 + t) * cout + lane * kStemWgCh + k] = v;
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r0 = 16 * mt + g, c0 = 8 * nt + 2 * t;
+      atomicAdd(&red[r0 * 33 + c0], acc[mt][nt][0]);
+      atomicAdd(&red[r0 * 33 + c0 + 1], acc[mt][nt][1]);
+      atomicAdd(&red[(r0 + 8) * 33 + c0], acc[mt][nt][2]);
+      atomicAdd(&red[(r0 + 8) * 33 + c0 + 1], acc[mt][nt][3]);
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
-    float v = 0.f;
-    for (int wv = 0; wv < nwarps; ++wv) v += red[wv * 27 * cout + i];
-    partial[static_cast<size_t>(blockIdx.x) * 27 * cout + i] = v;
-  }
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x)
+    partial[static_cast<size_t>(blockIdx.x) * 27 * 32 + i] = red[(i / 32) * 33 + (i % 32)];
 }
 
 // dw[co][tap] = beta*dw + sum_blocks partial[block][tap][co]
@@ -622,7 +691,6 @@ int upload_head(const float* w, const float* b, int K, int cin, cudaStream_t st)
   return 0;
 }
 
-constexpr int kStemWgradBlocksPerSm = 3;
 constexpr int kHeadBwdBlocksPerSm = 2;
 
 }  // namespace
@@ -651,7 +719,7 @@ int spff_conv3d_stem_fwd(const float* x, const float* w, void* y, long long ldy,
 }
 
 size_t spff_conv3d_stem_wgrad_workspace(int cout) {
-  return static_cast<size_t>(spff::num_sms()) * spff::kStemWgradBlocksPerSm * 27 * cout * sizeof(float);
+  return static_cast<size_t>(spff::num_sms()) * spff::kSwgBlocksPerSm * 27 * cout * sizeof(float);
 }
 
 int spff_conv3d_stem_wgrad(const float* x, const void* dy, long long lddy, int cout, spff_shape s, float* dw,
@@ -664,9 +732,10 @@ int spff_conv3d_stem_wgrad(const float* x, const void* dy, long long lddy, int c
     return SPFF_ERR_WORKSPACE;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int blocks = spff::num_sms() * spff::kStemWgradBlocksPerSm;
-  spff::stem_wgrad_kernel<<<blocks, 256, 8 * 27 * cout * sizeof(float), st>>>(x, static_cast<const bf16*>(dy), lddy,
-                                                                              cout, s, static_cast<float*>(workspace));
+  const int blocks = spff::num_sms() * spff::kSwgBlocksPerSm;
+  SPFF_REQUIRE(lddy % 8 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "conv3d_stem_wgrad: dy must be 16-byte aligned");
+  spff::stem_wgrad_mma_kernel<<<blocks, spff::kSwgWarps * 32, 0, st>>>(x, static_cast<const bf16*>(dy), lddy, s,
+                                                                      static_cast<float*>(workspace));
   spff::stem_wgrad_reduce_kernel<<<(27 * cout + 127) / 128, 128, 0, st>>>(static_cast<const float*>(workspace), blocks,
                                                                          cout, beta, dw);
   SPFF_CUDA(cudaGetLastError());

@@ -215,7 +215,7 @@ def test_pool_fwd_bwd():
     assert rel(ncdhw(sb2), yr.grad) < 1e-6
 
 
-@pytest.mark.parametrize("n,d,h,w", [(2, 5, 16, 16), (1, 5, 7, 9), (1, 3, 4, 4)])
+@pytest.mark.parametrize("n,d,h,w", [(2, 5, 16, 16), (1, 5, 7, 9), (1, 3, 4, 4), (1, 5, 8, 136), (2, 5, 128, 128)])
 def test_stem(n, d, h, w):
     from spff_b200 import ops
     torch.manual_seed(0)
@@ -229,10 +229,15 @@ def test_stem(n, d, h, w):
     dyb = pm(dy)
     dw = torch.full((32, 1, 3, 3, 3), float("nan"), device="cuda")
     ops.conv3d_stem_wgrad(x, dyb, 32, dw, 0.0)
+    # the tensor-core weight gradient reads x rounded to bf16: exact against that, 2^-9-close to fp32 x
+    xq = x.to(torch.bfloat16).double()
+    refq = torch.nn.grad.conv3d_weight(xq, (32, 1, 3, 3, 3), ncdhw(dyb).double(), padding=1).float()
     refw = torch.nn.grad.conv3d_weight(x.double(), (32, 1, 3, 3, 3), ncdhw(dyb).double(), padding=1).float()
-    assert rel(dw, refw) < 1e-4
+    print("stem wgrad rel vs bf16-x", rel(dw, refq), "vs fp32-x", rel(dw, refw))
+    assert rel(dw, refq) < 1e-4
+    assert rel(dw, refw) < 4e-3
     ops.conv3d_stem_wgrad(x, dyb, 32, dw, 1.0)
-    assert rel(dw, 2 * refw) < 1e-4
+    assert rel(dw, 2 * refq) < 1e-4
 
 
 @pytest.mark.parametrize("n,d,h,w,cin,cout", [(2, 5, 8, 8, 64, 32), (1, 5, 4, 4, 128, 64), (1, 5, 2, 2, 256, 128),
