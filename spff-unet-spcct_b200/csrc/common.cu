@@ -129,6 +129,8 @@ TileGeom make_tile_geom(const int ext[4], int rows) {
 
 static int g_debug_ctas = 0;
 int debug_ctas() { return g_debug_ctas; }
+static long long g_debug_flags[8] = {0};
+int debug_flag(int key) { return (key >= 0 && key < 8) ? static_cast<int>(g_debug_flags[key]) : 0; }
 
 }  // namespace spff
 
@@ -159,6 +161,10 @@ int spff_device_check(void) {
 int spff_debug_set(int key, long long value) {
   if (key == 0) {
     spff::g_debug_ctas = static_cast<int>(value);
+    return 0;
+  }
+  if (key > 0 && key < 8) {
+    spff::g_debug_flags[key] = value;
     return 0;
   }
   spff::set_error("unknown debug key %d", key);

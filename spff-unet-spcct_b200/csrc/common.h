@@ -16,6 +16,8 @@ int check_cuda(cudaError_t e, const char* what);
 int num_sms();
 // test hook (spff_debug_set key 0): CTA count override for persistent kernels, 0 = one per SM
 int debug_ctas();
+// test hook (spff_debug_set key >= 1): generic integer flags, 0 by default. key 1: disable the all-kh wgrad variant
+int debug_flag(int key);
 // K chunk (channels per TMA box) the conv3 kernels use for a GEMM-K channel count: 64 or 32
 int conv3_kc(int gemm_k_channels);
 
