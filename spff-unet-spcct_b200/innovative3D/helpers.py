@@ -15,6 +15,7 @@ There is no CPU path: CPU tensors raise.
 from __future__ import annotations
 
 import math
+import weakref
 from typing import List, Optional
 
 import numpy as np
@@ -48,19 +49,27 @@ def _prep(logits: torch.Tensor, labels: torch.Tensor):
 
 
 class _TallyCache:
-    key = None
+    """Tally of the most recent (logits, labels) pair, so that the loss and the metrics of one step
+    share one kernel pass. A hit needs the SAME live tensor objects at the same version — data_ptr
+    alone is not an identity (the caching allocator hands a freed block to the next tensor)."""
+    logits_ref = None
+    labels_ref = None
+    versions = None
+    ign = None
     tally: Optional[LossTally] = None
 
 
 def _tally(logits: torch.Tensor, labels: torch.Tensor, ignore_index: Optional[int]) -> LossTally:
     ign = _NO_IGNORE if ignore_index is None else int(ignore_index)
-    key = (logits.data_ptr(), logits._version, tuple(logits.shape), labels.data_ptr(), labels._version, ign)
-    if _TallyCache.key == key:
-        return _TallyCache.tally
+    c = _TallyCache
+    if (c.tally is not None and c.logits_ref is not None and c.logits_ref() is logits and c.labels_ref() is labels
+            and c.versions == (logits._version, labels._version) and c.ign == ign):
+        return c.tally
     lg, lb = _prep(logits, labels)
     t = LossTally(lg.shape[1], lg.device)
     ops.ce_confusion(lg, lb, ign, t.nll, t.count, t.confusion)
-    _TallyCache.key, _TallyCache.tally = key, t
+    c.logits_ref, c.labels_ref = weakref.ref(logits), weakref.ref(labels)
+    c.versions, c.ign, c.tally = (logits._version, labels._version), ign, t
     return t
 
 
@@ -68,8 +77,7 @@ class _CrossEntropyFn(torch.autograd.Function):
     """F.cross_entropy(logits, labels, ignore_index) (mean over valid voxels), helpers.py:798-801."""
 
     @staticmethod
-    def forward(ctx, logits, labels, ignore_index):
-        t = _tally(logits, labels, ignore_index)
+    def forward(ctx, logits, labels, ignore_index, t):
         ctx.save_for_backward(logits, labels, t.count)
         ctx.ignore_index = ignore_index
         return (t.nll[0] / t.count[0].double()).to(torch.float32)   # 0/0 = nan when nothing is valid, as torch
@@ -80,7 +88,7 @@ class _CrossEntropyFn(torch.autograd.Function):
         lg, lb = _prep(logits, labels)
         dl = torch.empty_like(lg)
         ops.ce_grad(lg, lb, int(ctx.ignore_index), count, g.detach().reshape(1).float().contiguous(), dl)
-        return dl.view_as(logits).to(logits.dtype), None, None
+        return dl.view_as(logits).to(logits.dtype), None, None, None
 
 
 def _dice_from_tally(t: LossTally, smooth: float) -> torch.Tensor:
@@ -104,8 +112,9 @@ def ce_plus_macro_dice_loss(logits, labels, num_classes, ignore_index=255, smoot
     gradient in the reference (argmax + .item()); here it stays on the device, so the call does not
     synchronise the host."""
     ign = _NO_IGNORE if ignore_index is None else int(ignore_index)
-    ce = _CrossEntropyFn.apply(logits, labels, ign)
-    dice = _dice_from_tally(_tally(logits, labels, ign), smooth)
+    t = _tally(logits, labels, ign)        # one pass; per_class_metrics_3d on the same tensors reuses it
+    ce = _CrossEntropyFn.apply(logits, labels, ign, t)
+    dice = _dice_from_tally(t, smooth)
     return ce + (0.5 * (1.0 - dice)).to(torch.float32)
 
 

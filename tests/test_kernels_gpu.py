@@ -373,3 +373,19 @@ def test_adam():
         opt.step()
         ops.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, step)
     assert torch.allclose(p, ref.detach(), atol=1e-6, rtol=1e-5)
+
+
+def test_loss_tally_cache_is_keyed_by_tensor_identity():
+    """Two different logits tensors that happen to reuse the same device block must not share a tally."""
+    from innovative3D import helpers as H
+    torch.manual_seed(0)
+    lab = torch.randint(0, 13, (1, 5, 8, 8), device="cuda")
+    vals = []
+    for scale in (1.0, 5.0):
+        logits = torch.randn(1, 13, 5, 8, 8, device="cuda") * scale      # freed each iteration -> same block next time
+        vals.append((float(H.ce_plus_macro_dice_loss(logits, lab, 13)), float(F.cross_entropy(logits, lab)),
+                     H.per_class_metrics_3d(logits, lab, 13, ignore_index=255)[3]))
+        del logits
+    assert abs(vals[0][0] - vals[1][0]) > 0.1
+    for loss, ce, _ in vals:
+        assert loss >= ce - 1e-5 and loss <= ce + 0.5 + 1e-5
