@@ -37,6 +37,9 @@ VARIANTS = {
     "E_SP_UNet": dict(names=("pre", "body"), efilm=True, fgate=False, se=True),       # models.py:1565-1573
     "FG_SP_UNet": dict(names=("pre", "body"), efilm=False, fgate=True, se=True),      # models.py:1575-1583
     "PlainCore_UNet": dict(names=("b1", "b2"), efilm=False, fgate=False, se=False),   # models.py:1594-1607
+    # LitSPCT_SEspec: plain blocks + SpectralSE + ChannelSE, input replicate-padded to multiples of 16 in
+    # (D,H,W) and the logits centre-cropped back (_LitSPCT_Base.forward, models.py:703-712, 1585-1592)
+    "SP_UNet": dict(names=("b1", "b2"), efilm=False, fgate=False, se=True, pad=16),
 }
 BLOCKS = ("enc1", "enc2", "enc3", "bott", "dec3", "dec2", "dec1")
 
@@ -167,7 +170,37 @@ def _channel_se(p: Params, pre: str, x: torch.Tensor) -> torch.Tensor:
     return x * torch.sigmoid(F.conv3d(h, p[f"{pre}.fc.2.weight"], p[f"{pre}.fc.2.bias"]))
 
 
+def pad_to_mult(x: torch.Tensor, m: int):
+    """_pad_to_mult_3d (models.py:109-120): replicate-pad [B,C,D,H,W] so that D, H, W are multiples of m,
+    the odd element of an uneven split on the right. Returns (x_pad, (D,H,W)) or (x, None)."""
+    _, _, d, h, w = x.shape
+    pd, ph, pw = (-d) % m, (-h) % m, (-w) % m
+    if not (pd or ph or pw):
+        return x, None
+    x = F.pad(x, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2, pd // 2, pd - pd // 2), mode="replicate")
+    return x, (d, h, w)
+
+
+def center_crop(x: torch.Tensor, orig):
+    """_center_crop_to_3d (models.py:122-127)."""
+    if orig is None:
+        return x
+    d, h, w = orig
+    sd, sh, sw = (x.shape[2] - d) // 2, (x.shape[3] - h) // 2, (x.shape[4] - w) // 2
+    return x[:, :, sd:sd + d, sh:sh + h, sw:sw + w]
+
+
 def unet_forward(p: Params, x: torch.Tensor, variant: str = "SPFF-UNet", taps: Dict[str, torch.Tensor] | None = None
+                 ) -> torch.Tensor:
+    """Variant forward: the core (below), wrapped in pad / crop for the variants that pad (SP_UNet)."""
+    m = VARIANTS[variant].get("pad")
+    if not m:
+        return core_forward(p, x, variant, taps)
+    xp, orig = pad_to_mult(x, m)
+    return center_crop(core_forward(p, xp, variant, taps), orig)
+
+
+def core_forward(p: Params, x: torch.Tensor, variant: str = "SPFF-UNet", taps: Dict[str, torch.Tensor] | None = None
                  ) -> torch.Tensor:
     """UNet3D_SpectralCore.forward (models.py:693-701) with the blocks of the given variant:
     _DoubleConvSpectral_Novel.forward (:1473-1478) or _DoubleConvSpectral (:620-625), `_post`

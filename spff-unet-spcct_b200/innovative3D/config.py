@@ -94,6 +94,8 @@ _add_variant("E_SP_UNet", build_class("LitSPCT_EnergyFiLM", **_SPCT_COMMON), Mul
              CHECKPOINT_DIR / "E_SP_UNet")                                         # config.py:433-438
 _add_variant("FG_SP_UNet", build_class("LitSPCT_FourierGate", **_SPCT_COMMON), MultiDicomDataModule3D,
              CHECKPOINT_DIR / "FG_SP_UNet")                                        # config.py:443-448
+_add_variant("SP_UNet", build_class("LitSPCT_SEspec", num_classes=NUM_CLASSES, lr=BEST_LR), MultiDicomDataModule3D,
+             CHECKPOINT_DIR / "SP_UNet")                                           # config.py:451-456
 _add_variant("PlainCore_UNet",
              build_class("LitSPCT_ControlUNet", **{**_SPCT_COMMON, "use_se": False, "use_specse": False}),
              MultiDicomDataModule3D, CHECKPOINT_DIR / "PlainCore_UNet")            # config.py:460-476

@@ -13,8 +13,8 @@ parameter containers and the whole graph — forward, and backward through one a
 scheduled by `spff_b200.engine.SpffEngine` onto libspff_b200.so. There is no eager fallback: on
 anything but an sm_100 device `forward` raises.
 
-In scope (SURVEY.md §8a): LitSPCT_EFiLM_FourierGate ("SPFF-UNet"), LitSPCT_EnergyFiLM, LitSPCT_FourierGate,
-LitSPCT_ControlUNet ("PlainCore_UNet"). Options of the reference core that no in-scope variant turns on
+In scope (SURVEY.md §8a, §8f-3): LitSPCT_EFiLM_FourierGate ("SPFF-UNet"), LitSPCT_EnergyFiLM, LitSPCT_FourierGate,
+LitSPCT_SEspec ("SP_UNet", depth padded 5 -> 16), LitSPCT_ControlUNet ("PlainCore_UNet"). Options of the reference core that no in-scope variant turns on
 (`use_spatial`, `use_skip_gate`, `ksd != 3`, non-instance norms, `use_moe`) raise NotImplementedError.
 """
 from __future__ import annotations
@@ -495,6 +495,75 @@ class BaseLitModel(pl.LightningModule):
     def step_metrics(self, tally: LossTally, total_voxels: int):
         """per_class_metrics_3d's 9-tuple from a fit_step tally (one device->host copy)."""
         return metrics_from_confusion(tally.confusion.cpu().numpy(), total_voxels)
+
+
+def _next_mult(n: int, m: int = 16) -> int:
+    return ((n + m - 1) // m) * m
+
+
+def _pad_to_mult_3d(x: torch.Tensor, m: int = 16):
+    """Replicate-pad [B,C,D,H,W] so that D/H/W are multiples of m (models.py:109-120); (x_pad, (D,H,W)) or (x, None)."""
+    if x.ndim != 5:
+        raise ValueError(f"expect [B,C,D,H,W], got {tuple(x.shape)}")
+    _, _, D, H, W = x.shape
+    pd, ph, pw = _next_mult(D, m) - D, _next_mult(H, m) - H, _next_mult(W, m) - W
+    if not (pd or ph or pw):
+        return x, None
+    x = torch.nn.functional.pad(x, (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2, pd // 2, pd - pd // 2), mode="replicate")
+    return x, (D, H, W)
+
+
+def _center_crop_to_3d(x: torch.Tensor, orig_dhw):
+    """models.py:122-127."""
+    if orig_dhw is None:
+        return x
+    D, H, W = orig_dhw
+    sd, sh, sw = (x.shape[2] - D) // 2, (x.shape[3] - H) // 2, (x.shape[4] - W) // 2
+    return x[:, :, sd:sd + D, sh:sh + H, sw:sw + W]
+
+
+_pad_to_mult16_3d = _pad_to_mult16 = _pad_to_mult_3d
+_center_crop_3d = _center_crop = _center_crop_to_3d
+
+
+class _LitSPCT_Base(BaseLitModel):
+    """Pads the input to multiples of `pad_multiple` in (D,H,W) — the 5 energy bins become 16 planes — runs
+    the core and centre-crops the logits (models.py:703-712). The pad / crop are tiny tensor ops around the
+    engine's autograd node; `fit_step` pads the labels with ignore_index instead of cropping the logits."""
+
+    def __init__(self, num_classes=NUM_CLASSES, lr=BEST_LR, pad_multiple: int = 16):
+        super().__init__(num_classes=num_classes, lr=lr, is_3d=True)
+        self._pad_multiple = int(pad_multiple)
+
+    def forward(self, x):
+        x = _pick_first_if_seq(x)
+        if x.ndim == 4:
+            x = x.unsqueeze(1)
+        x_pad, orig = _pad_to_mult16_3d(x.float(), self._pad_multiple)
+        return _center_crop_3d(self.model(x_pad), orig)
+
+    def fit_step(self, batch, optimize: bool = True, sample_group: Optional[int] = None):
+        imgs, lbls = batch if isinstance(batch, (list, tuple)) else (batch["image"], batch["label"])
+        imgs, lbls = _pick_first_if_seq(imgs), _pick_first_if_seq(lbls)
+        if imgs.ndim == 4:
+            imgs = imgs.unsqueeze(1)
+        x_pad, orig = _pad_to_mult16_3d(imgs.float(), self._pad_multiple)
+        if orig is not None:   # voxels outside the crop carry no loss: label them ignore_index
+            D, H, W = orig
+            full = torch.full((lbls.shape[0],) + tuple(x_pad.shape[2:]), IGNORE_INDEX, dtype=torch.int64, device=lbls.device)
+            sd, sh, sw = (x_pad.shape[2] - D) // 2, (x_pad.shape[3] - H) // 2, (x_pad.shape[4] - W) // 2
+            full[:, sd:sd + D, sh:sh + H, sw:sw + W] = lbls
+            lbls = full
+        return super().fit_step((x_pad, lbls), optimize=optimize, sample_group=sample_group)
+
+
+class LitSPCT_SEspec(_LitSPCT_Base):
+    """"SP_UNet": plain double-conv blocks + Channel-SE + Spectral-SE at all encoder stages (models.py:1585-1592)."""
+
+    def __init__(self, num_classes=NUM_CLASSES, lr=BEST_LR, base=32, pad_multiple=16):
+        super().__init__(num_classes=num_classes, lr=lr, pad_multiple=pad_multiple)
+        self.model = UNet3D_SpectralCore(in_channels=1, num_classes=num_classes, base=base, ksd=3, use_se=True,
+                                         use_specse=True, use_spatial=False, use_skip_gate=False)
 
 
 class LitSPCT_EFiLM_FourierGate(BaseLitModel):

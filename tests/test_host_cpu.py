@@ -46,7 +46,7 @@ def test_no_gpu_is_an_error_not_a_fallback():
 def test_variants_registry_surface():
     from innovative3D import config as C
     names = [v[0] for v in C.VARIANTS]
-    assert names[:1] == ["SPFF-UNet"] and {"E_SP_UNet", "FG_SP_UNet", "PlainCore_UNet"} <= set(names)
+    assert names[:1] == ["SPFF-UNet"] and {"E_SP_UNet", "FG_SP_UNet", "SP_UNet", "PlainCore_UNet"} <= set(names)
     assert (C.NUM_CLASSES, C.NUM_FRAMES, C.IGNORE_INDEX, C.BATCH_SIZE, C.BEST_LR, C.SEEDS) == (13, 5, 255, 1, 1e-4, [42, 123, 999])
     for name, builder, dm, ckpt in C.VARIANTS:
         lit = builder()
