@@ -32,6 +32,7 @@ except ImportError:  # not in this image: a minimal stand-in with the same metho
 
 from spff_b200 import dp, ops
 from spff_b200.engine import LossTally, NetConfig, SpffEngine, StagedBatch
+from spff_b200.sched import PlateauLR
 
 from .config import BEST_LR, IGNORE_INDEX, NUM_CLASSES, NUM_FRAMES
 from .helpers import (LOSS_REGISTRY, ce_plus_macro_dice_loss, metrics_from_confusion, per_class_metrics_2d,
@@ -487,6 +488,23 @@ class BaseLitModel(pl.LightningModule):
                 core.engine.invalidate_weights()   # written behind torch's back: re-pack the bf16 operands
             loss = st["tally"].loss()
         return {"loss": loss, "tally": st["tally"]}
+
+    def fused_lr_step(self, val_macro_dice: float) -> float:
+        """ReduceLROnPlateau(mode='max', factor=0.5, patience=5) on `val_macro_dice` for the fused Adam
+        (the schedule `configure_optimizers` hands to Lightning, models.py:593-594). Returns the new lr."""
+        if getattr(self, "_plateau", None) is None:
+            self._plateau = PlateauLR(float(self.hparams.lr), mode="max", factor=0.5, patience=5)
+        self.hparams["lr"] = self._plateau.step(val_macro_dice)
+        return self.hparams["lr"]
+
+    @torch.no_grad()
+    def predict_labels_sharded(self, x) -> tuple:
+        """Inference over a scan whose slices are independent units: this rank runs the
+        contiguous shard `dp.shard_range(len(x))` of the slices and returns ((lo, hi), uint8 labels
+        [hi-lo,F,H,W]). No collective: the caller concatenates shards in rank order."""
+        x = _pick_first_if_seq(x)
+        lo, hi = dp.shard_range(x.shape[0])
+        return (lo, hi), self.model.predict_labels(x[lo:hi])
 
     def fused_grads(self) -> Dict[str, torch.Tensor]:
         """Gradient views (by core parameter name) of the last fit_step."""

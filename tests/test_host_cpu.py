@@ -130,3 +130,19 @@ def test_shard_range_partitions():
             assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
             sizes = [hi - lo for lo, hi in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_plateau_lr_matches_torch_scheduler():
+    """PlateauLR == torch ReduceLROnPlateau(mode='max', factor=0.5, patience=5) on the same metric series."""
+    from spff_b200.sched import PlateauLR
+    import random
+    rnd = random.Random(0)
+    series = [0.1, 0.2, 0.25] + [0.25 + rnd.uniform(-0.02, 0.00001) for _ in range(40)] + [0.6] + [0.5] * 20
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=1e-4)
+    sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="max", factor=0.5, patience=5)
+    mine = PlateauLR(1e-4, mode="max", factor=0.5, patience=5)
+    for v in series:
+        sch.step(v)
+        assert mine.step(v) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12, abs=0)
+    assert mine.lr < 1e-4
