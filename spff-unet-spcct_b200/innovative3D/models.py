@@ -320,6 +320,17 @@ class UNet3D_SpectralCore(nn.Module):
         if self._engine is not None:
             self._engine.invalidate_weights()
 
+    def decoder_range(self):
+        """[lo, hi) of the flat buffer holding up3 .. out (transposed convs, decoder blocks, head): contiguous
+        because parameters are laid out in registration order (enc1..bott, up3, dec3, up2, dec2, up1, dec1, out, se)."""
+        names = [n for n in self._slots if n.split(".")[0] in ("up3", "dec3", "up2", "dec2", "up1", "dec1", "out")
+                 and not n.endswith("freq_mask")]
+        lo = min(self._slots[n][0] for n in names)
+        hi = max(self._slots[n][0] + (self._slots[n][1] + 3) // 4 * 4 for n in names)
+        inside = [n for n, (o, k, _) in self._slots.items() if lo <= o < hi]
+        assert sorted(inside) == sorted(names), "decoder parameters are not contiguous in the flat buffer"
+        return lo, hi
+
     # -- forward ---------------------------------------------------------------------------------
     def forward(self, x):
         x = _pick_first_if_seq(x)
@@ -477,9 +488,23 @@ class BaseLitModel(pl.LightningModule):
         st["grad"].zero_()
         st["tally"].zero()
         with torch.no_grad():
+            # data parallel: the head/decoder range of the flat gradient buffer is final while the last group's
+            # encoder backward still runs -> its all-reduce is issued there (async, NCCL stream) and overlaps
+            # it; the encoder-side ranges follow at the end. Still ONE bucket layout, two collectives in flight.
+            lo, hi = core.decoder_range()
+            pending = []
+            hook = None
+            if dp.world()[1] > 1:
+                hook = lambda: pending.append(dp.allreduce_async(st["grad"][lo:hi]))
             core.engine.train_step(imgs, lbls, st["G"], st["tally"], group=group, ignore_index=IGNORE_INDEX,
-                                   staged=staged)
-            gscale = dp.allreduce_grads(st["grad"])
+                                   staged=staged, decoder_done=hook)
+            if pending:
+                gscale = dp.allreduce_grads(st["grad"][:lo])
+                dp.allreduce_grads(st["grad"][hi:])
+                for w in pending:
+                    w.wait()
+            else:
+                gscale = dp.allreduce_grads(st["grad"])
             if optimize:
                 st["step"] += 1
                 n = core._n_eager

@@ -30,6 +30,13 @@ def allreduce_grads(flat_grad: torch.Tensor) -> float:
     return 1.0 / n
 
 
+def allreduce_async(flat_grad_range: torch.Tensor):
+    """Start the sum all-reduce of one contiguous range of the flat gradient buffer and return the work
+    handle (wait() before the optimizer). With NCCL the collective runs on its own stream after the
+    kernels already enqueued, i.e. concurrently with whatever the compute stream is given next."""
+    return dist.all_reduce(flat_grad_range, op=dist.ReduceOp.SUM, async_op=True)
+
+
 def allreduce_tally(nll: torch.Tensor, count: torch.Tensor, confusion: torch.Tensor) -> None:
     """Global loss statistics for logging (≈ 1.4 KB): sum of nll, valid voxels, confusion tally."""
     _, n = world()

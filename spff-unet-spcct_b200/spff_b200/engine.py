@@ -198,14 +198,17 @@ class GateTables:
         self.dbt: Dict[str, Optional[torch.Tensor]] = {}
         self.dkfg: Dict[str, Optional[torch.Tensor]] = {}
         self.leaves: Dict[str, torch.Tensor] = {}
-        self._live: List[torch.Tensor] = []     # tables with a graph, paired with self._grads
-        self._grads: List[torch.Tensor] = []
+        self._live: Dict[str, List[torch.Tensor]] = {b: [] for b in BLOCKS}    # tables with a graph, per block,
+        self._grads: Dict[str, List[torch.Tensor]] = {b: [] for b in BLOCKS}   # paired with their gradient accumulators
+        self._leaf_block: Dict[str, str] = {}
+        self._done: set = set()
 
         def leaf(name):
             t = params[name].detach()
             if need_grad:
                 t = t.clone().requires_grad_(True)
                 self.leaves[name] = t
+                self._leaf_block[name] = name.split(".")[0]
             return t
 
         with torch.set_grad_enabled(need_grad):
@@ -219,15 +222,15 @@ class GateTables:
                     self.g1[b], self.bt[b] = g1, bt
                     if need_grad:
                         self.dg1[b], self.dbt[b] = torch.zeros_like(g1), torch.zeros_like(bt)
-                        self._live += [g1, bt]
-                        self._grads += [self.dg1[b], self.dbt[b]]
+                        self._live[b] += [g1, bt]
+                        self._grads[b] += [self.dg1[b], self.dbt[b]]
                 if cfg.fgate:
                     k = tables.fourier_kernel(leaf(f"{b}.fgate.freq_mask"), leaf(f"{b}.fgate.mag_scale"), frames)
                     self.kfg[b] = k
                     if need_grad:
                         self.dkfg[b] = torch.zeros_like(k)
-                        self._live.append(k)
-                        self._grads.append(self.dkfg[b])
+                        self._live[b].append(k)
+                        self._grads[b].append(self.dkfg[b])
                 if cfg.chanse and b in _STAGE:
                     i = _STAGE[b]
                     w1 = params[f"se.{i}.fc.0.weight"].detach()
@@ -239,14 +242,18 @@ class GateTables:
     def _d(t):
         return t.detach() if t is not None else None
 
-    def finish(self, G: Dict[str, torch.Tensor]):
-        """G[name] += gradient of the EFiLM MLP / FourierGate parameters from the accumulated table
-        gradients (dg1, dbt, dkfg)."""
-        if not self._live:
+    def finish(self, G: Dict[str, torch.Tensor], blocks: Optional[Tuple[str, ...]] = None):
+        """G[name] += gradient of the EFiLM MLP / FourierGate parameters of `blocks` (default: every block
+        not finished yet) from the accumulated table gradients (dg1, dbt, dkfg)."""
+        todo = [b for b in (blocks or BLOCKS) if b not in self._done]
+        live = [t for b in todo for t in self._live[b]]
+        grads = [g for b in todo for g in self._grads[b]]
+        self._done.update(todo)
+        if not live:
             return
-        torch.autograd.backward(self._live, self._grads)
+        torch.autograd.backward(live, grads)
         for name, t in self.leaves.items():
-            if t.grad is not None:
+            if self._leaf_block[name] in todo and t.grad is not None:
                 G[name].add_(t.grad.view_as(G[name]))
 
 
@@ -407,7 +414,7 @@ class SpffEngine:
             ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.1"][1], dxin, cin)
 
     def backward_group(self, B: _GroupBuffers, T: GateTables, G: Dict[str, torch.Tensor],
-                       dlogits: Optional[torch.Tensor]):
+                       dlogits: Optional[torch.Tensor], after_decoder: Optional[Callable[[], None]] = None):
         """Accumulates (+=) every parameter gradient of this group into the fp32 tensors of `G`
         (shaped like the parameters). dlogits: fp32 [n,K,d,h,w], or None when the fused head/loss
         kernel already left the head's input gradient in B.gout[1] (and its dW/db in G)."""
@@ -425,6 +432,10 @@ class SpffEngine:
             ops.convt_k122_wgrad(xb, 2 * cu, dy, cu, G[f"{up}.weight"], 1.0)
             ops.in_stats(dy, cu, B.b64.get(B.idx[f"{up}.bstats"]))
             ops.convt_k122_dgrad(dy, cu, self._packed[up][1], B.gout[l + 1], 2 * cu)
+        if after_decoder is not None:   # head / decoder / transposed-conv gradients of this group are complete
+            for up in ("up3", "up2", "up1"):
+                G[f"{up}.bias"].add_(B.b64.get(B.idx[f"{up}.bstats"])[:, :, 0].sum(0).float())
+            after_decoder()
         self._block_bwd(B, T, G, "bott", B.gout[4], B.pool[3], B.dpool[3])
         for l, enc in ((3, "enc3"), (2, "enc2"), (1, "enc1")):
             c = B.C[l]
@@ -435,8 +446,9 @@ class SpffEngine:
             else:
                 self._block_bwd(B, T, G, enc, dskip, None, None)
         # ConvTranspose3d bias gradient = column sums of dy (fp64 per-sample partials -> fp32 accumulate)
-        for up in ("up3", "up2", "up1"):
-            G[f"{up}.bias"].add_(B.b64.get(B.idx[f"{up}.bstats"])[:, :, 0].sum(0).float())
+        if after_decoder is None:
+            for up in ("up3", "up2", "up1"):
+                G[f"{up}.bias"].add_(B.b64.get(B.idx[f"{up}.bstats"])[:, :, 0].sum(0).float())
 
     # ------------------------------------------------------------------------------------------
     # batch-level drivers
@@ -497,12 +509,16 @@ class SpffEngine:
         T.finish(G)
 
     def train_step(self, x: torch.Tensor, labels: torch.Tensor, G: Dict[str, torch.Tensor], tally: "LossTally",
-                   group: int = 32, ignore_index: int = 255, staged: Optional["StagedBatch"] = None):
+                   group: int = 32, ignore_index: int = 255, staged: Optional["StagedBatch"] = None,
+                   decoder_done: Optional[Callable[[], None]] = None):
         """Fused forward + CE/confusion + backward over the batch in sample groups. Accumulates the
         parameter gradients of the batch-mean CE (helpers.py:798-801; the Dice term of the loss has
         no gradient, helpers.py:782-795) into G and the loss statistics into `tally`.
         `staged`: the batch is still arriving from pinned host memory on a copy stream (StagedBatch);
-        each group's forward waits only for its own slice."""
+        each group's forward waits only for its own slice.
+        `decoder_done`: called once, inside the LAST group's backward, as soon as every gradient of the
+        head, the decoder blocks and the transposed convs is final (data-parallel: their all-reduce
+        then overlaps the encoder's backward)."""
         x = self._check_input(x)
         bsz, _, d, h, w = x.shape
         if labels.shape != (bsz, d, h, w):
@@ -525,7 +541,13 @@ class SpffEngine:
             ops.head_loss_fused(B.out["dec1"], p["out.weight"], p["out.bias"], labels[lo:hi], ignore_index, n_valid, None,
                                 tally.nll, tally.count, tally.confusion, B.gout[1],
                                 G["out.weight"].view(-1, self.cfg.base), G["out.bias"], 1.0)
-            self.backward_group(B, T, G, None)
+            last = hi == bsz
+            hook = None
+            if last and decoder_done is not None:
+                def hook():
+                    T.finish(G, ("dec3", "dec2", "dec1"))
+                    decoder_done()
+            self.backward_group(B, T, G, None, after_decoder=hook)
         T.finish(G)
 
 
