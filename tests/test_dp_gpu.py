@@ -58,4 +58,7 @@ def test_two_rank_step_equals_single_process_step():
     assert torch.equal(out[0]["grad"], out[1]["grad"])
     assert rel(out[0]["grad"] / world, g1) < 2e-3
     assert torch.equal(out[0]["flat"], out[1]["flat"])
-    assert rel(out[0]["flat"], lit.model._flat.detach().cpu()) < 1e-4
+    # Adam's first step moves every weight by ~lr * sign(g): near-zero gradients may flip sign between the two
+    # summation orders, so parameters agree to within 2 lr element-wise (and closely in the mean)
+    diff = (out[0]["flat"] - lit.model._flat.detach().cpu()).abs()
+    assert float(diff.max()) <= 2.1e-3 and float((diff > 1e-4).float().mean()) < 0.05
