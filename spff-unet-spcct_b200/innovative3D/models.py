@@ -40,7 +40,7 @@ from .helpers import (LOSS_REGISTRY, ce_plus_macro_dice_loss, metrics_from_confu
 
 LOG_PER_CLASS = os.getenv("LOG_PER_CLASS", "1") == "1"
 # samples per group of the engine's schedule (activations of one group live at a time in fit_step)
-SAMPLE_GROUP = int(os.getenv("SPFF_SAMPLE_GROUP", "128"))
+SAMPLE_GROUP = int(os.getenv("SPFF_SAMPLE_GROUP", "256"))
 
 
 def _pick_first_if_seq(x):
