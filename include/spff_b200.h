@@ -128,9 +128,12 @@ int spff_in_coeffs_from_partials(const float* partial, int slots, const float* g
 /* y = lrelu(x*A + B) (bf16 -> bf16). */
 int spff_norm_act_apply(const void* x, long long ldx, const float* coef, void* y, long long ldy, int c, spff_shape s,
                         float slope, void* stream);
-/* S[n][d][c] += sum_{h,w} lrelu(x*A + B)  (fp32; caller zeroes S). */
+/* S[n][d][c] = sum_{h,w} lrelu(x*A + B)  (fp32). With a workspace of spff_norm_act_reduce_workspace() bytes
+ * the block partials are reduced in a fixed order and S is overwritten (bit-reproducible); with
+ * workspace == NULL the blocks accumulate into S with atomics (+=; the caller zeroes S). */
+size_t spff_norm_act_reduce_workspace(int c, spff_shape s);
 int spff_norm_act_reduce(const void* x, long long ldx, const float* coef, float* S, int c, spff_shape s, float slope,
-                         void* stream);
+                         void* workspace, size_t workspace_bytes, void* stream);
 /* y = lrelu(x*A+B)*P + Q; P,Q are [n][d][c] fp32 or both NULL (identity). If ypool != NULL also
  * writes the (1,2,2) max-pool of y (nn.MaxPool3d, models.py:658-665) to ypool [n,d,h/2,w/2] with pitch ldp. */
 int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, const float* P, const float* Q,
@@ -145,9 +148,12 @@ int spff_gate_micro_fwd(const float* S, const float* g1, const float* bt, const 
                         spff_shape s, float* P, float* Q, void* stream);
 /* Backward pass 1: R[n][d][c][6] += per-plane sums over (h,w) of
  *   {dout*a, dout, dout*m, m, dout*m*xhat, m*xhat},  m = lrelu'(z), z = x*A+B, a = lrelu(z).
- * plain != 0: only slots 2 and 4 are produced (all that spff_gate_micro_bwd(flags = 0) reads). */
+ * plain != 0: only slots 2 and 4 are produced (all that spff_gate_micro_bwd(flags = 0) reads).
+ * workspace as for spff_norm_act_reduce: fixed-order overwrite of the produced slots, or NULL for atomics (+=). */
+size_t spff_norm_act_bwd_reduce_workspace(int c, spff_shape s, int plain);
 int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
-                             float* R, int c, spff_shape s, float slope, int plain, void* stream);
+                             float* R, int c, spff_shape s, float slope, int plain, void* workspace,
+                             size_t workspace_bytes, void* stream);
 /* Backward micro-kernel: consumes R (and S), recomputes the gates, produces
  *   bcoef[n][c] = {gamma*rstd, mean(dz), mean(dz*xhat), 0}, dSa[n][d][c], Pout[n][d][c]
  * and ACCUMULATES (+=) dgamma[c], dbeta[c], dg1[c][d], dbt[c][d], dkfg[d], dse_*. flags == 0 is the

@@ -95,6 +95,7 @@ __device__ __forceinline__ float reduce_rows_fetch(const float* red, int c8, int
   return t;
 }
 __device__ __forceinline__ bool fast_reduce_ok(int c8) { return c8 <= 32 && (c8 & (c8 - 1)) == 0; }
+inline bool fast_reduce_ok_host(int c8) { return c8 <= 32 && (c8 & (c8 - 1)) == 0; }
 
 // ---------------------------------------------------------------------------------------------
 // InstanceNorm statistics: stats[n][c] += {sum x, sum x^2} over the block's positions (double).
@@ -236,7 +237,8 @@ template <bool WRITE, bool REDUCE, bool AFFINE>
 __global__ void __launch_bounds__(kBlock)
 norm_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ coef,
                 const float* __restrict__ P, const float* __restrict__ Q, __nv_bfloat16* __restrict__ y,
-                long long ldy, float* __restrict__ S, PlaneGrid g, int d, int c, float slope) {
+                long long ldy, float* __restrict__ S, PlaneGrid g, int d, int c, float slope,
+                float* __restrict__ part = nullptr /* REDUCE: [plane][chunk][c] block partials instead of atomics */) {
   extern __shared__ float red[];
   const int n = blockIdx.z, dd = blockIdx.y;
   const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
@@ -280,8 +282,14 @@ norm_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float*
     if (fast_reduce_ok(g.c8)) {
       reduce_rows_fast<8>(acc, red, g.c8);
       const int L = g.c8 < 32 ? g.c8 : 32;
-      if (threadIdx.x < L * 8)
-        atomicAdd(S + (static_cast<long long>(n) * d + dd) * c + threadIdx.x, reduce_rows_fetch<8>(red, g.c8, threadIdx.x));
+      if (threadIdx.x < L * 8) {
+        const float t = reduce_rows_fetch<8>(red, g.c8, threadIdx.x);
+        const long long plane = static_cast<long long>(n) * d + dd;
+        if (part)
+          part[(plane * gridDim.x + blockIdx.x) * c + threadIdx.x] = t;
+        else
+          atomicAdd(S + plane * c + threadIdx.x, t);
+      }
       return;
     }
     reduce_rows<8>(acc, red, g.c8, g.rpi);
@@ -602,7 +610,7 @@ template <bool PLAIN>
 __global__ void __launch_bounds__(kBlock, PLAIN ? 4 : 3)
 norm_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ x,
                             long long ldx, const float* __restrict__ coef, float* __restrict__ R, PlaneGrid4 g, int d,
-                            int c, float slope) {
+                            int c, float slope, float* __restrict__ part /* [plane][chunk][c][NK] or null (atomics) */) {
   extern __shared__ float red[];
   constexpr int NK = PLAIN ? 2 : 6;
   const int n = blockIdx.z, dd = blockIdx.y;
@@ -666,7 +674,13 @@ norm_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long ld
   for (int k = 0; k < NK; ++k) {
     const int slot = PLAIN ? (k == 0 ? 2 : 4) : k;
     reduce_cv<4>(acc[k], red, g.cv);
-    for (int idx = threadIdx.x; idx < nout; idx += kBlock) atomicAdd(Rp + idx * 6 + slot, reduce_cv_fetch<4>(red, g.cv, idx));
+    for (int idx = threadIdx.x; idx < nout; idx += kBlock) {
+      const float t = reduce_cv_fetch<4>(red, g.cv, idx);
+      if (part)
+        part[(((static_cast<long long>(n) * d + dd) * gridDim.x + blockIdx.x) * c + idx) * NK + k] = t;
+      else
+        atomicAdd(Rp + idx * 6 + slot, t);
+    }
     __syncthreads();
   }
 }
@@ -731,6 +745,21 @@ norm_act_bwd_apply4_kernel(const __nv_bfloat16* __restrict__ dout, long long ldd
       }
     }
   }
+}
+
+// Fixed-order second stage of the plane reductions: out[(plane*c + ch)*out_stride + slot0 + k*slot_step] =
+// sum over the plane's chunks of part[((plane*chunks + chunk)*c + ch)*nk + k]  (overwrites: no zeroing,
+// no atomics -> bit-reproducible S and R).
+__global__ void sum_chunks_kernel(const float* __restrict__ part, int chunks, int c, int nk, float* __restrict__ out,
+                                  int out_stride, int slot0, int slot_step, long long total) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int k = static_cast<int>(i % nk);
+  const int ch = static_cast<int>((i / nk) % c);
+  const long long plane = i / (static_cast<long long>(nk) * c);
+  float t = 0.f;
+  for (int q = 0; q < chunks; ++q) t += part[((plane * chunks + q) * c + ch) * nk + k];
+  out[(plane * c + ch) * out_stride + slot0 + k * slot_step] = t;
 }
 
 // grid for the 4-channel kernels; returns false when the channel count does not fit them
@@ -841,16 +870,31 @@ int spff_norm_act_apply(const void* x, long long ldx, const float* coef, void* y
   return 0;
 }
 
+size_t spff_norm_act_reduce_workspace(int c, spff_shape s) {
+  PlaneGrid g;
+  dim3 grid;
+  if (c <= 0 || s.n <= 0 || s.d <= 0 || s.h <= 0 || s.w <= 0) return 0;
+  if (spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid) || !spff::fast_reduce_ok_host(g.c8)) return 0;
+  return static_cast<size_t>(s.n) * s.d * grid.x * c * sizeof(float);
+}
+
 int spff_norm_act_reduce(const void* x, long long ldx, const float* coef, float* S, int c, spff_shape s, float slope,
-                         void* stream) {
+                         void* workspace, size_t workspace_bytes, void* stream) {
   SPFF_ENTRY_CHECK();
   PlaneGrid g;
   dim3 grid;
   int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
   if (e) return e;
-  spff::norm_act_kernel<false, true, false>
-      <<<grid, kBlock, 8 * kBlock * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-          static_cast<const bf16*>(x), ldx, coef, nullptr, nullptr, nullptr, 0, S, g, s.d, c, slope);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t need = spff_norm_act_reduce_workspace(c, s);
+  float* part = (workspace && need > 0 && workspace_bytes >= need) ? static_cast<float*>(workspace) : nullptr;
+  SPFF_REQUIRE(!workspace || part, "norm_act_reduce: workspace too small or channel count without a fixed-order path");
+  spff::norm_act_kernel<false, true, false><<<grid, kBlock, 8 * kBlock * sizeof(float), st>>>(
+      static_cast<const bf16*>(x), ldx, coef, nullptr, nullptr, nullptr, 0, S, g, s.d, c, slope, part);
+  if (part) {
+    const long long total = static_cast<long long>(s.n) * s.d * c;
+    spff::sum_chunks_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(part, grid.x, c, 1, S, 1, 0, 1, total);
+  }
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }
@@ -889,8 +933,17 @@ int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, 
   return 0;
 }
 
+size_t spff_norm_act_bwd_reduce_workspace(int c, spff_shape s, int plain) {
+  spff::PlaneGrid4 g4;
+  dim3 grid;
+  if (c <= 0 || s.n <= 0 || s.d <= 0 || s.h <= 0 || s.w <= 0) return 0;
+  if (!spff::make_grid4(c, static_cast<long long>(s.h) * s.w, s, &g4, &grid)) return 0;
+  return static_cast<size_t>(s.n) * s.d * grid.x * c * (plain ? 2 : 6) * sizeof(float);
+}
+
 int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
-                             float* R, int c, spff_shape s, float slope, int plain, void* stream) {
+                             float* R, int c, spff_shape s, float slope, int plain, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   SPFF_ENTRY_CHECK();
   PlaneGrid g;
   dim3 grid;
@@ -899,16 +952,26 @@ int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, lo
     if (spff::make_grid4(c, static_cast<long long>(s.h) * s.w, s, &g4, &grid)) {
       cudaStream_t st4 = static_cast<cudaStream_t>(stream);
       const size_t smem = 8 * 32 * 4 * sizeof(float);
+      const size_t need = spff_norm_act_bwd_reduce_workspace(c, s, plain);
+      float* part = (workspace && workspace_bytes >= need) ? static_cast<float*>(workspace) : nullptr;
+      SPFF_REQUIRE(!workspace || part, "norm_act_bwd_reduce: workspace too small");
       if (plain)
         spff::norm_act_bwd_reduce4_kernel<true><<<grid, kBlock, smem, st4>>>(
-            static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g4, s.d, c, slope);
+            static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g4, s.d, c, slope, part);
       else
         spff::norm_act_bwd_reduce4_kernel<false><<<grid, kBlock, smem, st4>>>(
-            static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g4, s.d, c, slope);
+            static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g4, s.d, c, slope, part);
+      if (part) {
+        const int nk = plain ? 2 : 6;
+        const long long total = static_cast<long long>(s.n) * s.d * c * nk;
+        spff::sum_chunks_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st4>>>(part, grid.x, c, nk, R, 6, plain ? 2 : 0,
+                                                                                       plain ? 2 : 1, total);
+      }
       SPFF_CUDA(cudaGetLastError());
       return 0;
     }
   }
+  SPFF_REQUIRE(!workspace, "norm_act_bwd_reduce: this channel count has no fixed-order path (pass no workspace)");
   int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
   if (e) return e;
   if (plain)

@@ -234,20 +234,25 @@ stem_wgrad_mma_kernel(const float* __restrict__ x, const __nv_bfloat16* __restri
       __syncwarp();
     }
   }
-  // block reduction of the eight 32 x 32 accumulators (row = tap, column = channel)
+  // block reduction of the eight 32 x 32 accumulators (row = tap, column = channel): the warps add
+  // their fragments one after the other, so the summation order is fixed (bit-reproducible)
   for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
+  for (int wv = 0; wv < kSwgWarps; ++wv) {
+    if (warp == wv) {
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int r0 = 16 * mt + g, c0 = 8 * nt + 2 * t;
-      atomicAdd(&red[r0 * 33 + c0], acc[mt][nt][0]);
-      atomicAdd(&red[r0 * 33 + c0 + 1], acc[mt][nt][1]);
-      atomicAdd(&red[(r0 + 8) * 33 + c0], acc[mt][nt][2]);
-      atomicAdd(&red[(r0 + 8) * 33 + c0 + 1], acc[mt][nt][3]);
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r0 = 16 * mt + g, c0 = 8 * nt + 2 * t;
+          red[r0 * 33 + c0] += acc[mt][nt][0];
+          red[r0 * 33 + c0 + 1] += acc[mt][nt][1];
+          red[(r0 + 8) * 33 + c0] += acc[mt][nt][2];
+          red[(r0 + 8) * 33 + c0 + 1] += acc[mt][nt][3];
+        }
     }
-  __syncthreads();
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x)
     partial[static_cast<size_t>(blockIdx.x) * 27 * 32 + i] = red[(i / 32) * 33 + (i % 32)];
 }

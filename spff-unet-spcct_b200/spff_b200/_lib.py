@@ -59,10 +59,12 @@ _PROTOTYPES = {
     "spff_in_coeffs": [_P, _P, _P, c_float, c_int, c_int, _LL, c_int, _P, _P],
     "spff_in_coeffs_from_partials": [_P, c_int, _P, _P, c_float, c_int, c_int, _LL, _P, _P],
     "spff_norm_act_apply": [_P, _LL, _P, _P, _LL, c_int, Shape, c_float, _P],
-    "spff_norm_act_reduce": [_P, _LL, _P, _P, c_int, Shape, c_float, _P],
+    "spff_norm_act_reduce_workspace": [c_int, Shape],
+    "spff_norm_act_reduce": [_P, _LL, _P, _P, c_int, Shape, c_float, _P, c_size_t, _P],
     "spff_norm_act_affine_apply": [_P, _LL, _P, _P, _P, _P, _LL, _P, _LL, c_int, Shape, c_float, _P],
     "spff_gate_micro_fwd": [_P] * 8 + [c_int, c_int, c_int, Shape, _P, _P, _P],
-    "spff_norm_act_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, c_int, Shape, c_float, c_int, _P],
+    "spff_norm_act_bwd_reduce_workspace": [c_int, Shape, c_int],
+    "spff_norm_act_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, c_int, Shape, c_float, c_int, _P, c_size_t, _P],
     "spff_gate_micro_bwd": [_P] * 11 + [c_int, c_int, c_int, Shape] + [_P] * 12 + [_P],
     "spff_norm_act_bwd_apply": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _LL, c_int, Shape, c_float, _P],
     "spff_maxpool_bwd_add": [_P, _LL, _P, _LL, _P, _LL, c_int, Shape, c_int, _P],
@@ -79,7 +81,8 @@ _PROTOTYPES = {
 }
 
 _SIZE_T_FUNCS = {"spff_conv3d_k3_wgrad_workspace", "spff_conv3d_stem_wgrad_workspace",
-                 "spff_convt_k122_wgrad_workspace", "spff_head_bwd_workspace", "spff_head_loss_workspace"}
+                 "spff_convt_k122_wgrad_workspace", "spff_head_bwd_workspace", "spff_head_loss_workspace",
+                 "spff_norm_act_reduce_workspace", "spff_norm_act_bwd_reduce_workspace"}
 
 
 def _declare():

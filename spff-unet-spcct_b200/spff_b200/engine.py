@@ -341,7 +341,7 @@ class SpffEngine:
         P = Q = None
         if flags:
             S = B.f32.get(B.idx[f"{b}.S"])
-            ops.norm_act_reduce(B.x2[b], B.coef[f"{b}.2"], S, c, SLOPE)
+            ops.norm_act_reduce(B.x2[b], B.coef[f"{b}.2"], S, c, SLOPE, fixed_order=True)
             P, Q = B.P[b], B.Q[b]
             ops.gate_micro_fwd(S, T._d(T.g1[b]), T._d(T.bt[b]), T._d(T.kfg[b]), T.se[b], flags, c, shp, P, Q)
         ops.norm_act_affine_apply(B.x2[b], B.coef[f"{b}.2"], P, Q, B.out[b], pool_to, c, SLOPE)
@@ -383,7 +383,7 @@ class SpffEngine:
         t1, t2 = B.t1[l], B.t2[l]
         # tail + IN2 + lrelu backward
         R2 = B.b32.get(B.idx[f"{b}.R2"])
-        ops.norm_act_bwd_reduce(dout, B.x2[b], B.coef[f"{b}.2"], R2, c, SLOPE, plain=(flags == 0))
+        ops.norm_act_bwd_reduce(dout, B.x2[b], B.coef[f"{b}.2"], R2, c, SLOPE, plain=(flags == 0), fixed_order=True)
         S = B.f32.get(B.idx[f"{b}.S"]) if flags else None
         dse = None
         if flags & GATE_CHANSE:
@@ -401,7 +401,7 @@ class SpffEngine:
         ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.2"][1], t2, c)
         # IN1 + lrelu backward
         R1 = B.b32.get(B.idx[f"{b}.R1"])
-        ops.norm_act_bwd_reduce(t2, B.x1[b], B.coef[f"{b}.1"], R1, c, SLOPE, plain=True)
+        ops.norm_act_bwd_reduce(t2, B.x1[b], B.coef[f"{b}.1"], R1, c, SLOPE, plain=True, fixed_order=True)
         ops.gate_micro_bwd(R1, None, B.coef[f"{b}.1"], p[f"{b}.{cn1}.1.weight"], None, None, None, None, 0, c, shp,
                            B.bcoef[f"{b}.1"], None, None, G[f"{b}.{cn1}.1.weight"], G[f"{b}.{cn1}.1.bias"], None, None,
                            None, None)

@@ -186,9 +186,16 @@ def norm_act_apply(x, coef, y, c, slope):
     call("spff_norm_act_apply", ptr(x), ldx, ptr(coef), ptr(y), ldy, c, s, float(slope), stream_ptr())
 
 
-def norm_act_reduce(x, coef, S, c, slope):
+def norm_act_reduce(x, coef, S, c, slope, fixed_order=False):
+    """fixed_order=True: S is overwritten by a bit-reproducible two-stage reduction (no zeroing needed);
+    otherwise the blocks accumulate into S with atomics (zero S first)."""
     s, ldx = _view(x, c)
-    call("spff_norm_act_reduce", ptr(x), ldx, ptr(coef), ptr(S), c, s, float(slope), stream_ptr())
+    ws, nbytes = None, 0
+    if fixed_order:
+        nbytes = int(_lib.lib.spff_norm_act_reduce_workspace(c, s))
+        ws = workspace(nbytes, x.device) if nbytes else None
+    call("spff_norm_act_reduce", ptr(x), ldx, ptr(coef), ptr(S), c, s, float(slope), ptr(ws), ws.numel() if ws is not None else 0,
+         stream_ptr())
 
 
 def norm_act_affine_apply(x, coef, P, Q, y, ypool, c, slope):
@@ -206,12 +213,16 @@ def gate_micro_fwd(S, g1, bt, kfg, se, flags, c, shape, P, Q):
          shape, ptr(P), ptr(Q), stream_ptr())
 
 
-def norm_act_bwd_reduce(dout, x, coef, R, c, slope, plain=False):
+def norm_act_bwd_reduce(dout, x, coef, R, c, slope, plain=False, fixed_order=False):
     """plain=True: only the two sums the gate-free InstanceNorm + LeakyReLU backward needs."""
     s, lddo = _view(dout, c)
     _, ldx = _view(x, c)
+    ws, nbytes = None, 0
+    if fixed_order:
+        nbytes = int(_lib.lib.spff_norm_act_bwd_reduce_workspace(c, s, int(plain)))
+        ws = workspace(nbytes, x.device) if nbytes else None
     call("spff_norm_act_bwd_reduce", ptr(dout), lddo, ptr(x), ldx, ptr(coef), ptr(R), c, s, float(slope), int(plain),
-         stream_ptr())
+         ptr(ws), ws.numel() if ws is not None else 0, stream_ptr())
 
 
 def gate_micro_bwd(R, S, coef, gamma, g1, bt, kfg, se, flags, c, shape, bcoef, dSa, Pout, dgamma, dbeta, dg1, dbt, dkfg,
