@@ -52,7 +52,8 @@ const char* spff_last_error(void);
 /* 0 when the current CUDA device is sm_100 (B200); SPFF_ERR_UNSUPPORTED_ARCH otherwise. */
 int spff_device_check(void);
 /* test hook. key 0: number of CTAs for persistent kernels (0 = one per SM); key 1: non-zero disables the
- * all-kh variant of the 32-channel weight-gradient kernel. */
+ * all-kh variant of the 32-channel weight-gradient kernel; key 2: non-zero selects the CUDA-core fused head kernel
+ * instead of the mma.sync one. */
 int spff_debug_set(int key, long long value);
 
 /* ---- 3x3x3 convolution, stride 1, zero pad 1, no bias ----------------------------------------

@@ -26,6 +26,10 @@ __constant__ float c_head_b[kMaxK];
 __device__ __forceinline__ uint32_t smem_u32_local(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ uint32_t pack_bf16x2_local(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -660,6 +664,317 @@ head_loss_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const void*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tensor-core version of the fused training head (same contract as head_loss_kernel above, which stays
+// as the reference implementation behind spff_debug_set(2, 1)). The three tiny contractions of the head
+//   logits[16 pos x 16 cls] = x[16 x 32] . W^T,   dx[16 x 32] = dl[16 x 16] . W,   dW[16 x 32] += dl^T . x
+// run as warp-level mma.sync m16n8k16 tiles of 16 positions; softmax / CE / arg-max / confusion work on
+// the accumulator fragments (a position's 16 logits live in the 4 lanes of a quad). fp32 accuracy is
+// kept by splitting the fp32 operands into bf16 hi + lo parts (W for the logits and dx, dl for dx and dW):
+// x is bf16 already, so logits carry ~2^-17 relative error and the loss, the tallies and the gradients
+// match the CUDA-core kernel to fp32 rounding.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHmWarps = 8;
+constexpr int kHmBlocksPerSm = 2;
+constexpr int kHmXPitch = 40;   // bf16 per staged x / dx row (32 + 8 pad)
+constexpr int kHmDPitch = 24;   // bf16 per staged dl row (16 + 8 pad)
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16(v0), h1 = __float2bfloat16(v1);
+  const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __bfloat162float(h0), v1 - __bfloat162float(h1));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <typename LabelT>
+__global__ void __launch_bounds__(kHmWarps * 32, kHmBlocksPerSm)
+head_loss_mma_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const void* __restrict__ labels, int ignore_index,
+                     int K, long long total, const unsigned long long* __restrict__ n_valid,
+                     const float* __restrict__ gscale, double* __restrict__ acc, unsigned long long* __restrict__ counts,
+                     unsigned long long* __restrict__ confusion, __nv_bfloat16* __restrict__ dx, long long lddx,
+                     float* __restrict__ partial /* [block][K*32 + K] */) {
+  __shared__ __align__(16) __nv_bfloat16 xs[kHmWarps][16][kHmXPitch];
+  __shared__ __align__(16) __nv_bfloat16 os[kHmWarps][16][kHmXPitch];
+  __shared__ __align__(16) __nv_bfloat16 dls[kHmWarps][2][16][kHmDPitch];
+  __shared__ float red[kMaxK * kHeadC + kMaxK];
+  __shared__ unsigned int s_conf[kMaxK * kMaxK];
+  __shared__ float s_nll[kHmWarps];
+  __shared__ unsigned int s_cnt[kHmWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x) s_conf[i] = 0;
+  for (int i = threadIdx.x; i < kMaxK * kHeadC + kMaxK; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const unsigned long long nv = n_valid[0];
+  const float scale = (nv > 0 ? 1.f / static_cast<float>(nv) : 0.f) * (gscale ? gscale[0] : 1.f);
+
+  // weight fragments (constant memory -> registers), classes >= K are zero
+  auto wv = [&](int k, int c) -> float { return k < K ? c_head_w[k * kHeadC + c] : 0.f; };
+  uint32_t wl_hi[2][2][2], wl_lo[2][2][2];   // logits: [class tile][k step][b0,b1]: B[k=ch][n=class]
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cls = 8 * nt + g, ch = 16 * ks + 8 * h + 2 * t;
+        split_bf16x2(wv(cls, ch), wv(cls, ch + 1), wl_hi[nt][ks][h], wl_lo[nt][ks][h]);
+      }
+  uint32_t wd_hi[4][2], wd_lo[4][2];          // dx: [channel tile][b0,b1]: B[k=class][n=ch]
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cls = 8 * h + 2 * t, ch = 8 * j + g;
+      split_bf16x2(wv(cls, ch), wv(cls + 1, ch), wd_hi[j][h], wd_lo[j][h]);
+    }
+  float bias[2][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) bias[nt][e] = (8 * nt + 2 * t + e) < K ? c_head_b[8 * nt + 2 * t + e] : 0.f;
+
+  float dwacc[4][4], dbp[2][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dwacc[j][e] = 0.f;
+  dbp[0][0] = dbp[0][1] = dbp[1][0] = dbp[1][1] = 0.f;
+  float nll_sum = 0.f;
+  unsigned int cnt = 0;
+
+  const long long ntiles = (total + 15) / 16;
+  const long long tstep = static_cast<long long>(gridDim.x) * kHmWarps;
+  // software prefetch: the x rows and the labels of the NEXT tile are requested before the current one is
+  // computed, so the two global round trips per tile overlap the tensor-core work instead of preceding it
+  uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = nx0;
+  int nlab[2] = {ignore_index, ignore_index};
+  auto fetch = [&](long long tile) {
+    nx0 = nx1 = make_uint4(0, 0, 0, 0);
+    nlab[0] = nlab[1] = ignore_index;
+    if (tile >= ntiles) return;
+    const long long q0 = tile * 16;
+    const int pos = lane >> 1, half = lane & 1;
+    if (q0 + pos < total) {
+      const uint4* src = reinterpret_cast<const uint4*>(x + (q0 + pos) * ldx + half * 16);
+      nx0 = __ldg(src);
+      nx1 = __ldg(src + 1);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+      if (q0 + g + 8 * rr < total) nlab[rr] = static_cast<int>(static_cast<const LabelT*>(labels)[q0 + g + 8 * rr]);
+  };
+  fetch(static_cast<long long>(blockIdx.x) * kHmWarps + warp);
+  for (long long tile = static_cast<long long>(blockIdx.x) * kHmWarps + warp; tile < ntiles; tile += tstep) {
+    const long long p0 = tile * 16;
+    const int clab[2] = {nlab[0], nlab[1]};
+    {  // stage 16 positions x 32 channels (zeros past the end)
+      const int pos = lane >> 1, half = lane & 1;
+      uint4* dst = reinterpret_cast<uint4*>(&xs[warp][pos][half * 16]);
+      dst[0] = nx0;
+      dst[1] = nx1;
+    }
+    fetch(tile + tstep);
+    __syncwarp();
+    // ---- logits
+    float l[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      l[nt][0] = l[nt][2] = bias[nt][0];
+      l[nt][1] = l[nt][3] = bias[nt][1];
+    }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t a[4];
+      const int mi = lane >> 3, r = lane & 7;
+      const uint32_t addr = smem_u32_local(&xs[warp][r + 8 * (mi & 1)][16 * ks + 8 * (mi >> 1)]);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        mma_bf16_16816(l[nt], a, wl_hi[nt][ks]);
+        mma_bf16_16816(l[nt], a, wl_lo[nt][ks]);
+      }
+    }
+    // ---- per-row softmax / CE / arg-max: row g (values [nt][0..1]) and row g + 8 (values [nt][2..3])
+    float dl[2][4];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const long long pos = p0 + g + 8 * rr;
+      const bool inb = pos < total;
+      const int lab = clab[rr];
+      const bool valid = inb && lab != ignore_index;
+      float v[4];
+      int cls[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        cls[q] = 8 * (q >> 1) + 2 * t + (q & 1);
+        v[q] = cls[q] < K ? l[q >> 1][2 * rr + (q & 1)] : -INFINITY;
+      }
+      float mx = v[0];
+      int arg = cls[0];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (v[q] > mx) {   // ascending class order inside the thread: strict > keeps the first maximum
+          mx = v[q];
+          arg = cls[q];
+        }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (om > mx || (om == mx && oa < arg)) {
+          mx = om;
+          arg = oa;
+        }
+      }
+      float e[4], se = 0.f, ll = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        e[q] = cls[q] < K ? __expf(v[q] - mx) : 0.f;
+        se += e[q];
+        if (cls[q] == lab) ll = v[q];
+      }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        se += __shfl_xor_sync(0xffffffffu, se, o);
+        ll += __shfl_xor_sync(0xffffffffu, ll, o);
+      }
+      if (valid && t == 0) {
+        nll_sum += (mx + __logf(se)) - ll;
+        ++cnt;
+        if (lab >= 0 && lab < K) atomicAdd(&s_conf[lab * K + arg], 1u);
+      }
+      const float inv = 1.f / se;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float gq = 0.f;
+        if (valid && cls[q] < K) gq = (e[q] * inv - (cls[q] == lab ? 1.f : 0.f)) * scale;
+        dl[q >> 1][2 * rr + (q & 1)] = gq;
+        dbp[q >> 1][q & 1] += gq;
+      }
+    }
+    // ---- dl as bf16 hi + lo A fragments (row g | row g+8, classes 2t.. | 8+2t..)
+    uint32_t ah[4], al[4];
+    split_bf16x2(dl[0][0], dl[0][1], ah[0], al[0]);
+    split_bf16x2(dl[0][2], dl[0][3], ah[1], al[1]);
+    split_bf16x2(dl[1][0], dl[1][1], ah[2], al[2]);
+    split_bf16x2(dl[1][2], dl[1][3], ah[3], al[3]);
+    // ---- dx = dl . W  -> staged, then 16-byte coalesced stores
+    if (dx) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(o, ah, wd_hi[j]);
+        mma_bf16_16816(o, al, wd_hi[j]);
+        mma_bf16_16816(o, ah, wd_lo[j]);
+        *reinterpret_cast<uint32_t*>(&os[warp][g][8 * j + 2 * t]) = pack_bf16x2_local(o[0], o[1]);
+        *reinterpret_cast<uint32_t*>(&os[warp][g + 8][8 * j + 2 * t]) = pack_bf16x2_local(o[2], o[3]);
+      }
+    }
+    // ---- stage dl (hi, lo) for the transposed operand of dW
+    *reinterpret_cast<uint32_t*>(&dls[warp][0][g][2 * t]) = ah[0];
+    *reinterpret_cast<uint32_t*>(&dls[warp][0][g + 8][2 * t]) = ah[1];
+    *reinterpret_cast<uint32_t*>(&dls[warp][0][g][8 + 2 * t]) = ah[2];
+    *reinterpret_cast<uint32_t*>(&dls[warp][0][g + 8][8 + 2 * t]) = ah[3];
+    *reinterpret_cast<uint32_t*>(&dls[warp][1][g][2 * t]) = al[0];
+    *reinterpret_cast<uint32_t*>(&dls[warp][1][g + 8][2 * t]) = al[1];
+    *reinterpret_cast<uint32_t*>(&dls[warp][1][g][8 + 2 * t]) = al[2];
+    *reinterpret_cast<uint32_t*>(&dls[warp][1][g + 8][8 + 2 * t]) = al[3];
+    __syncwarp();
+    if (dx) {
+      const int pos = lane >> 1, half = lane & 1;
+      if (p0 + pos < total) {
+        const uint4* src = reinterpret_cast<const uint4*>(&os[warp][pos][half * 16]);
+        uint4* dst = reinterpret_cast<uint4*>(dx + (p0 + pos) * lddx + half * 16);
+        dst[0] = src[0];
+        dst[1] = src[1];
+      }
+    }
+    // ---- dW[class][ch] += dl^T . x   (A = dl^T through ldmatrix.trans, B = x through ldmatrix.trans)
+    {
+      const int mi = lane >> 3, r = lane & 7;
+      uint32_t th[4], tl[4];
+      const uint32_t ad_hi = smem_u32_local(&dls[warp][0][r + 8 * (mi >> 1)][8 * (mi & 1)]);
+      const uint32_t ad_lo = smem_u32_local(&dls[warp][1][r + 8 * (mi >> 1)][8 * (mi & 1)]);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(th[0]), "=r"(th[1]), "=r"(th[2]), "=r"(th[3]) : "r"(ad_hi));
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(tl[0]), "=r"(tl[1]), "=r"(tl[2]), "=r"(tl[3]) : "r"(ad_lo));
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t bx[4];
+        const uint32_t ax = smem_u32_local(&xs[warp][r + 8 * (mi & 1)][8 * (2 * h2 + (mi >> 1))]);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(bx[0]), "=r"(bx[1]), "=r"(bx[2]), "=r"(bx[3]) : "r"(ax));
+        const uint32_t b0[2] = {bx[0], bx[1]}, b1[2] = {bx[2], bx[3]};
+        mma_bf16_16816(dwacc[2 * h2], th, b0);
+        mma_bf16_16816(dwacc[2 * h2], tl, b0);
+        mma_bf16_16816(dwacc[2 * h2 + 1], th, b1);
+        mma_bf16_16816(dwacc[2 * h2 + 1], tl, b1);
+      }
+    }
+    __syncwarp();
+  }
+  // ---- block reduction in a fixed order (warp after warp): dW fragments (row = class g | g+8, col = 8j + 2t..), db
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float v = dbp[nt][e];
+      for (int o = 4; o <= 16; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      dbp[nt][e] = v;
+    }
+  for (int o = 16; o > 0; o >>= 1) {
+    nll_sum += __shfl_xor_sync(0xffffffffu, nll_sum, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+    s_nll[warp] = nll_sum;
+    s_cnt[warp] = cnt;
+  }
+  for (int wvv = 0; wvv < kHmWarps; ++wvv) {
+    if (warp == wvv) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        red[g * kHeadC + 8 * j + 2 * t] += dwacc[j][0];
+        red[g * kHeadC + 8 * j + 2 * t + 1] += dwacc[j][1];
+        red[(g + 8) * kHeadC + 8 * j + 2 * t] += dwacc[j][2];
+        red[(g + 8) * kHeadC + 8 * j + 2 * t + 1] += dwacc[j][3];
+      }
+      if (g == 0) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) red[kMaxK * kHeadC + 8 * nt + 2 * t + e] += dbp[nt][e];
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < K * kHeadC + K; i += blockDim.x) {
+    const int src = i < K * kHeadC ? i : kMaxK * kHeadC + (i - K * kHeadC);
+    partial[static_cast<size_t>(blockIdx.x) * (K * kHeadC + K) + i] = red[src];
+  }
+  if (threadIdx.x == 0) {
+    double tt = 0;
+    unsigned long long c = 0;
+    for (int wvv = 0; wvv < kHmWarps; ++wvv) {
+      tt += s_nll[wvv];
+      c += s_cnt[wvv];
+    }
+    atomicAdd(acc, tt);
+    atomicAdd(counts, c);
+  }
+  for (int i = threadIdx.x; i < K * K; i += blockDim.x)
+    if (s_conf[i]) atomicAdd(confusion + i, static_cast<unsigned long long>(s_conf[i]));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam semantics, no weight decay / amsgrad)
 // ---------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -871,7 +1186,17 @@ int spff_head_loss_fused(const void* x, long long ldx, int cin, const float* w, 
   auto nv = reinterpret_cast<const unsigned long long*>(n_valid);
   auto cnt = reinterpret_cast<unsigned long long*>(counts);
   auto conf = reinterpret_cast<unsigned long long*>(confusion);
-  if (label_bytes == 1)
+  if (spff::debug_flag(2) == 0) {   // tensor-core path (default); spff_debug_set(2, 1) selects the CUDA-core kernel
+    static_assert(spff::kHmBlocksPerSm == spff::kHeadLossBlocksPerSm, "the two kernels share the partial workspace");
+    if (label_bytes == 1)
+      spff::head_loss_mma_kernel<uint8_t><<<blocks, spff::kHmWarps * 32, 0, st>>>(
+          static_cast<const bf16*>(x), ldx, labels, ignore_index, k, total, nv, gscale, acc, cnt, conf,
+          static_cast<bf16*>(dx), lddx, static_cast<float*>(workspace));
+    else
+      spff::head_loss_mma_kernel<long long><<<blocks, spff::kHmWarps * 32, 0, st>>>(
+          static_cast<const bf16*>(x), ldx, labels, ignore_index, k, total, nv, gscale, acc, cnt, conf,
+          static_cast<bf16*>(dx), lddx, static_cast<float*>(workspace));
+  } else if (label_bytes == 1)
     spff::head_loss_kernel<uint8_t><<<blocks, spff::kHeadLossWarps * 32, 0, st>>>(
         static_cast<const bf16*>(x), ldx, labels, ignore_index, k, total, nv, gscale, acc, cnt, conf,
         static_cast<bf16*>(dx), lddx, static_cast<float*>(workspace));
