@@ -207,6 +207,49 @@ int spff_head_loss_fused(const void* x, long long ldx, int cin, const float* w, 
                          long long lddx, float* dw, float* db, float beta, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ---- "3DUNet" control: Cicek3DUNet + depth adapter (models.py:718-777; config.py:283-311) ---------------
+ * Its 3x3x3 convolutions, normalise + ReLU passes (slope 0), head and loss are the entry points above;
+ * the ones below are what only this variant needs. */
+/* ConvTranspose3d kernel = stride = (2,2,2) with bias (models.py:733-739). `s` = coarse grid; the fine
+ * tensors are [n, 2d, 2h, 2w, c]. Weight [cin][cout][2][2][2] fp32, packed like the (1,2,2) one with 8 taps. */
+int spff_pack_convt_weight_k222(const float* w, void* w_fwd, void* w_dgrad, int cin, int cout, void* stream);
+int spff_convt_k222_fwd(const void* x, long long ldx, int cin, const void* w_fwd, const float* bias, void* y,
+                        long long ldy, int cout, spff_shape s, void* stream);
+int spff_convt_k222_dgrad(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
+                          int cin, spff_shape s, void* stream);
+size_t spff_convt_k222_wgrad_workspace(int cin, int cout, spff_shape s);
+int spff_convt_k222_wgrad(const void* x, long long ldx, int cin, const void* dy, long long lddy, int cout,
+                          spff_shape s, float* dw, float beta, void* workspace, size_t workspace_bytes,
+                          void* stream);
+/* Depth-only resampling y[n][do][e] = sum_di matrix[do][di] * x[n][di][e] over `inner` contiguous elements per
+ * plane (bf16: elem_bytes 2, fp32: 4). F.interpolate(mode="trilinear", align_corners=False) with H, W unchanged
+ * (`_resize_depth_like` / `_resize_logits_depth_like`, models.py:153-163) is such a matrix; its backward is the
+ * same call with the transposed matrix. matrix: device fp32 [dout][din], din, dout <= 32. */
+int spff_depth_resample(const void* x, void* y, int elem_bytes, int n, int din, int dout, long long inner,
+                        const float* matrix, void* stream);
+/* BatchNorm3d(c) coefficients (models.py:721; F.batch_norm): batch statistics over (n, d, h, w) from either the
+ * conv epilogue's partials [n][slots][2][c] or spff_in_stats' stats [n][c][2] (exactly one non-NULL), summed in
+ * a fixed order in double; coef[k][c] = {A, B, mean, rstd} is written for every sample k (the layout the
+ * normalise kernels read). Training (eval == 0) also updates running_mean / running_var (momentum, unbiased
+ * variance; may be NULL). eval != 0: coefficients from the running statistics. count = d*h*w per sample. */
+size_t spff_bn_coeffs_workspace(int c);
+int spff_bn_coeffs(const float* partial, int slots, const double* stats, const float* gamma, const float* beta, float eps,
+                   int n, int c, long long count, float momentum, float* running_mean, float* running_var, int eval,
+                   float* coef, void* workspace, size_t workspace_bytes, void* stream);
+/* BatchNorm backward coefficients from R (slots 2 and 4 of spff_norm_act_bwd_reduce, plain mode):
+ * bcoef[k][c] = {gamma*rstd, mean(dz), mean(dz*xhat), 0} with BATCH means, dgamma[c] += , dbeta[c] += . */
+int spff_bn_bwd_coeffs(const float* R, const float* coef, const float* gamma, int c, spff_shape s, float* bcoef,
+                       float* dgamma, float* dbeta, void* stream);
+/* nn.MaxPool3d(2) (models.py:728-731): ypool [n, d/2, h/2, w/2, c]; backward scatters dpool to the first
+ * maximum of each 2x2x2 window of y and adds it to dskip (accumulate != 0) or overwrites dskip. `s` = full grid. */
+int spff_maxpool222_fwd(const void* y, long long ldy, void* ypool, long long ldp, int c, spff_shape s, void* stream);
+int spff_maxpool222_bwd_add(const void* dpool, long long ldp, const void* y, long long ldy, void* dskip, long long ldd, int c,
+                            spff_shape s, int accumulate, void* stream);
+/* torch.optim.SGD(lr, momentum, nesterov, weight_decay), dampening 0 (models.py:844-846). first_step != 0: the
+ * momentum buffer is initialised with the gradient. grad is scaled by grad_scale first (1/world under DP). */
+int spff_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
+                  float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
+
 /* ---- optimizer (models.py:591-594: torch.optim.Adam, lr 1e-4, betas (0.9,0.999), eps 1e-8) -------- */
 int spff_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float grad_scale, void* stream);

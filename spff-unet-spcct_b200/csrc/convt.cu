@@ -30,11 +30,13 @@ struct PwParams {
   long long ldo;
   int ho, wo;            // output grid extents
   int scale;             // 2 forward (rows scatter to 2h+i, 2w+j), 1 dgrad
+  int dscale;            // output planes per input plane: 2 for the (2,2,2) forward (plane 2d + (q >> 2)), else 1
+  int nfull, noff;       // rows of one packed weight block and the first row this launch reads (N-split of wide outputs)
   const float* bias;     // [N] or null
 };
 
 struct PwMaps {
-  CUtensorMap a[4];
+  CUtensorMap a[8];
   CUtensorMap b;
 };
 
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
             if (leader) {
               mbar_expect_tx(&full[s], bytes);
               tma_load_5d(st, &maps.a[t], &full[s], kc * KC, w0, h0, dd, n);
-              tma_load_2d(st + L::kABytes, &maps.b, &full[s], 0, blk * p.N);
+              tma_load_2d(st + L::kABytes, &maps.b, &full[s], 0, blk * p.nfull + p.noff);
             }
             if (++s == L::kStages) {
               s = 0;
@@ -173,10 +175,11 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
       decode(item, qo, w0, h0, dd, n);
       const int ww = w0 + m % p.bw, hh = h0 + m / p.bw;
       const bool ok = m < rows && ww < p.w && hh < p.h;
-      const int oh = hh * p.scale + (p.nquad > 1 ? (qo >> 1) : 0);
+      const int oh = hh * p.scale + (p.nquad > 1 ? ((qo >> 1) & 1) : 0);
       const int ow = ww * p.scale + (p.nquad > 1 ? (qo & 1) : 0);
+      const int od = dd * p.dscale + (p.nquad > 4 ? (qo >> 2) : 0);
       __nv_bfloat16* dst =
-          p.out + (((static_cast<long long>(n) * p.d + dd) * p.ho + oh) * p.wo + ow) * p.ldo;
+          p.out + (((static_cast<long long>(n) * p.d * p.dscale + od) * p.ho + oh) * p.wo + ow) * p.ldo;
       mbar_wait(&acc_full[buf], (accph >> buf) & 1u);
       accph ^= 1u << buf;
       tc_fence_after();
@@ -194,8 +197,8 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
           for (int c = 0; c < 32; c += 2) {
             float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
             if (p.bias) {
-              a += __ldg(p.bias + c0 + c);
-              b += __ldg(p.bias + c0 + c + 1);
+              a += __ldg(p.bias + p.noff + c0 + c);
+              b += __ldg(p.bias + p.noff + c0 + c + 1);
             }
             pk[c >> 1] = pack_bf16x2(a, b);
           }
@@ -234,14 +237,17 @@ void pick_tile(int h, int w, int max_rows, bool k16, int* bw_out, int* bh_out) {
 }
 
 // rank-5 map (c, w, h, d, n) of a position-major view whose (h, w) grid is sub-sampled by `scale`
-// starting at (oh, ow): the quadrant views of the fine grid.
-int encode_grid_map(CUtensorMap* m, const void* base, long long ld, int c, int n, int d, int hfull, int wfull, int scale,
-                    int oh, int ow, int box_c, int bw, int bh, int swizzle) {
-  const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(base) + (static_cast<long long>(oh) * wfull + ow) * ld;
+// starting at (oh, ow) — the quadrant views of the fine grid — and whose planes are sub-sampled by
+// `dscale` starting at `od` (the octant views of the (2,2,2) transposed conv; dfull = planes of the view).
+int encode_grid_map(CUtensorMap* m, const void* base, long long ld, int c, int n, int dfull, int hfull, int wfull, int scale,
+                    int oh, int ow, int box_c, int bw, int bh, int swizzle, int dscale = 1, int od = 0) {
+  const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(base) +
+                           ((static_cast<long long>(od) * hfull + oh) * wfull + ow) * ld;
   uint64_t dims[5] = {static_cast<uint64_t>(c), static_cast<uint64_t>(wfull / scale), static_cast<uint64_t>(hfull / scale),
-                      static_cast<uint64_t>(d), static_cast<uint64_t>(n)};
+                      static_cast<uint64_t>(dfull / dscale), static_cast<uint64_t>(n)};
   uint64_t str[4] = {static_cast<uint64_t>(ld) * 2 * scale, static_cast<uint64_t>(ld) * 2 * wfull * scale,
-                     static_cast<uint64_t>(ld) * 2 * wfull * hfull, static_cast<uint64_t>(ld) * 2 * wfull * hfull * d};
+                     static_cast<uint64_t>(ld) * 2 * wfull * hfull * dscale,
+                     static_cast<uint64_t>(ld) * 2 * wfull * hfull * dfull};
   uint32_t box[5] = {static_cast<uint32_t>(box_c), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1, 1};
   return encode_tmap_bf16(m, b, 5, dims, str, box, swizzle);
 }
@@ -268,10 +274,10 @@ int launch_pw(const PwMaps& maps, const PwParams& p, cudaStream_t st) {
 //   dgrad B[q][kc][ci][k] = W[ci][kc*KC'+k][q]     (N = cin,  K = cout, KC' = 64 / 32)
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_convt_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin, int cout,
-                                         int KC, int dgrad) {
+                                         int KC, int dgrad, int nq) {
   const int N = dgrad ? cin : cout, K = dgrad ? cout : cin;
   const int nkc = K / KC;
-  const long long total = 4LL * cin * cout;
+  const long long total = static_cast<long long>(nq) * cin * cout;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     long long r = i;
@@ -281,7 +287,7 @@ __global__ void pack_convt_weight_kernel(const float* __restrict__ w, __nv_bfloa
     const int q = static_cast<int>(r);
     const int kk = kc * KC + k;
     const int ci = dgrad ? nn : kk, co = dgrad ? kk : nn;
-    out[i] = __float2bfloat16(w[(static_cast<long long>(ci) * cout + co) * 4 + q]);
+    out[i] = __float2bfloat16(w[(static_cast<long long>(ci) * cout + co) * nq + q]);
   }
 }
 
@@ -438,8 +444,10 @@ __global__ void __launch_bounds__(kThreads, 1) pw_wgrad_kernel(const __grid_cons
 }
 
 // dW[ci][co][q] = beta*dW + sum_split partial
+// (nq, qoff): dW holds nq taps per (ci, co) and this launch produced taps [qoff, qoff + 4) — the (2,2,2) kernel
+// runs the four-quadrant contraction once per depth tap.
 __global__ void pw_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int cin, int cout,
-                                       int COB, int CIB, int ksplit, float beta) {
+                                       int COB, int CIB, int ksplit, float beta, int nq, int qoff) {
   const int SP = 128 / COB, NMMA = 4 / SP;
   const int ncib = cin / CIB;
   const long long total = 4LL * cin * cout;
@@ -455,7 +463,8 @@ __global__ void pw_wgrad_reduce_kernel(const float* __restrict__ partial, float*
     float acc = 0.f;
     for (int s = 0; s < ksplit; ++s)
       acc += partial[((static_cast<size_t>(item) * ksplit + s) * NMMA + i) * 128 * CIB + static_cast<size_t>(lane) * CIB + cic];
-    dw[e] = (beta == 0.f) ? acc : fmaf(beta, dw[e], acc);
+    float* dst = dw + (static_cast<long long>(ci) * cout + co) * nq + qoff + q;
+    *dst = (beta == 0.f) ? acc : fmaf(beta, *dst, acc);
   }
 }
 
@@ -499,6 +508,121 @@ int launch_pw_wgrad(const PwWgMaps& maps, const PwWgParams& p, int ctas, cudaStr
   return 0;
 }
 
+// ---- host-side launch plans shared by the (1,2,2) and (2,2,2) entry points --------------------------------
+// nd = 1: kernel = stride = (1,2,2), 4 taps; nd = 2: kernel = stride = (2,2,2), 8 taps (tap = (i*2 + j)*2 + k).
+int pack_convt_impl(const float* w, void* w_fwd, void* w_dgrad, int cin, int cout, int nq, cudaStream_t st) {
+  const long long total = static_cast<long long>(nq) * cin * cout;
+  const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
+  if (w_fwd)
+    pack_convt_weight_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_fwd), cin, cout, conv3_kc(cin), 0, nq);
+  if (w_dgrad)
+    pack_convt_weight_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_dgrad), cin, cout, conv3_kc(cout), 1,
+                                                     nq);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+void fill_tiles(PwParams* p, spff_shape s) {
+  p->n = s.n; p->d = s.d; p->h = s.h; p->w = s.w;
+  pick_tile(s.h, s.w, 128, false, &p->bw, &p->bh);
+  p->tiles_w = (s.w + p->bw - 1) / p->bw;
+  p->tiles_h = (s.h + p->bh - 1) / p->bh;
+  p->ntiles = static_cast<long long>(s.n) * s.d * p->tiles_w * p->tiles_h;
+}
+
+int encode_b_map(CUtensorMap* m, const void* w, int KC, long long rows, int box_rows) {
+  uint64_t dims[2] = {static_cast<uint64_t>(KC), static_cast<uint64_t>(rows)};
+  uint64_t str[1] = {static_cast<uint64_t>(KC) * 2};
+  uint32_t box[2] = {static_cast<uint32_t>(KC), static_cast<uint32_t>(box_rows)};
+  return encode_tmap_bf16(m, w, 2, dims, str, box, KC * 2);
+}
+
+// an output wider than 256 channels (one UMMA N) runs as several launches over 256-wide column blocks
+int pick_nchunk(int n) { return n <= 256 ? n : (n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : (n % 64 == 0 ? 64 : 32))); }
+
+int convt_fwd_impl(const void* x, long long ldx, int cin, const void* w_fwd, const float* bias, void* y, long long ldy,
+                   int cout, spff_shape s, int nd, cudaStream_t st) {
+  const int KC = conv3_kc(cin), nq = 4 * nd;
+  PwParams p{};
+  fill_tiles(&p, s);
+  p.nkc = cin / KC; p.ntap = 1; p.nquad = nq; p.nfull = cout;
+  p.ldo = ldy; p.ho = 2 * s.h; p.wo = 2 * s.w; p.scale = 2; p.dscale = nd; p.bias = bias;
+  PwMaps maps;
+  int e = encode_grid_map(&maps.a[0], x, ldx, cin, s.n, s.d, s.h, s.w, 1, 0, 0, KC, p.bw, p.bh, KC * 2);
+  if (e) return e;
+  const int nc = pick_nchunk(cout);
+  e = encode_b_map(&maps.b, w_fwd, KC, static_cast<long long>(nq) * p.nkc * cout, nc);
+  if (e) return e;
+  for (int noff = 0; noff < cout; noff += nc) {
+    p.N = nc; p.noff = noff;
+    p.out = static_cast<__nv_bfloat16*>(y) + noff;
+    e = KC == 64 ? launch_pw<64>(maps, p, st) : launch_pw<32>(maps, p, st);
+    if (e) return e;
+  }
+  return 0;
+}
+
+int convt_dgrad_impl(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx, int cin,
+                     spff_shape s, int nd, cudaStream_t st) {
+  const int KC = conv3_kc(cout), nq = 4 * nd;
+  PwParams p{};
+  fill_tiles(&p, s);
+  p.nkc = cout / KC; p.ntap = nq; p.nquad = 1; p.nfull = cin;
+  p.ldo = lddx; p.ho = s.h; p.wo = s.w; p.scale = 1; p.dscale = 1; p.bias = nullptr;
+  PwMaps maps;
+  int e;
+  for (int q = 0; q < nq; ++q) {
+    e = encode_grid_map(&maps.a[q], dy, lddy, cout, s.n, nd * s.d, 2 * s.h, 2 * s.w, 2, (q >> 1) & 1, q & 1, KC, p.bw, p.bh,
+                        KC * 2, nd, q >> 2);
+    if (e) return e;
+  }
+  const int nc = pick_nchunk(cin);
+  e = encode_b_map(&maps.b, w_dgrad, KC, static_cast<long long>(nq) * p.nkc * cin, nc);
+  if (e) return e;
+  for (int noff = 0; noff < cin; noff += nc) {
+    p.N = nc; p.noff = noff;
+    p.out = static_cast<__nv_bfloat16*>(dx) + noff;
+    e = KC == 64 ? launch_pw<64>(maps, p, st) : launch_pw<32>(maps, p, st);
+    if (e) return e;
+  }
+  return 0;
+}
+
+int convt_wgrad_impl(const void* x, long long ldx, int cin, const void* dy, long long lddy, int cout, spff_shape s,
+                     float* dw, float beta, void* workspace, size_t workspace_bytes, int nd, cudaStream_t st) {
+  const PwWgPlan pl = make_pw_plan(cin, cout, s);
+  if (workspace_bytes < pl.ws_bytes) {
+    set_error("convt wgrad: workspace %zu < %zu bytes", workspace_bytes, pl.ws_bytes);
+    return SPFF_ERR_WORKSPACE;
+  }
+  SPFF_REQUIRE((pl.bw * pl.bh) % 16 == 0 && pl.bw * pl.bh * pl.cob * 2 <= 8192, "convt wgrad: cannot tile %dx%d", s.h, s.w);
+  PwWgParams p{};
+  p.n = s.n; p.d = s.d; p.h = s.h; p.w = s.w; p.bw = pl.bw; p.bh = pl.bh; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
+  p.ntiles = pl.ntiles; p.ncob = pl.ncob; p.ncib = pl.ncib; p.ksplit = pl.ksplit;
+  p.partial = static_cast<float*>(workspace);
+  PwWgMaps maps;
+  int e = encode_grid_map(&maps.x, x, ldx, cin, s.n, s.d, s.h, s.w, 1, 0, 0, 64, pl.bw, pl.bh, 128);
+  if (e) return e;
+  const int ctas = pl.ncob * pl.ncib * pl.ksplit;
+  const long long total = 4LL * cin * cout;
+  for (int i = 0; i < nd; ++i) {   // depth tap
+    for (int q = 0; q < 4; ++q) {
+      e = encode_grid_map(&maps.dy[q], dy, lddy, cout, s.n, nd * s.d, 2 * s.h, 2 * s.w, 2, q >> 1, q & 1, pl.cob, pl.bw,
+                          pl.bh, pl.cob * 2, nd, i);
+      if (e) return e;
+    }
+    if (pl.cob == 64 && pl.cib == 128) e = launch_pw_wgrad<64, 128>(maps, p, ctas, st);
+    else if (pl.cob == 64) e = launch_pw_wgrad<64, 64>(maps, p, ctas, st);
+    else if (pl.cib == 128) e = launch_pw_wgrad<32, 128>(maps, p, ctas, st);
+    else e = launch_pw_wgrad<32, 64>(maps, p, ctas, st);
+    if (e) return e;
+    pw_wgrad_reduce_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(p.partial, dw, cin, cout, pl.cob, pl.cib,
+                                                                                  pl.ksplit, beta, 4 * nd, 4 * i);
+  }
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 }  // namespace spff
 
@@ -506,17 +630,12 @@ extern "C" {
 
 int spff_pack_convt_weight(const float* w, void* w_fwd, void* w_dgrad, int cin, int cout, void* stream) {
   SPFF_REQUIRE(w && cin % 32 == 0 && cout % 32 == 0, "pack_convt_weight: channels must be multiples of 32");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long total = 4LL * cin * cout;
-  const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  if (w_fwd)
-    spff::pack_convt_weight_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_fwd), cin, cout,
-                                                           spff::conv3_kc(cin), 0);
-  if (w_dgrad)
-    spff::pack_convt_weight_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_dgrad), cin, cout,
-                                                           spff::conv3_kc(cout), 1);
-  SPFF_CUDA(cudaGetLastError());
-  return 0;
+  return spff::pack_convt_impl(w, w_fwd, w_dgrad, cin, cout, 4, static_cast<cudaStream_t>(stream));
+}
+
+int spff_pack_convt_weight_k222(const float* w, void* w_fwd, void* w_dgrad, int cin, int cout, void* stream) {
+  SPFF_REQUIRE(w && cin % 32 == 0 && cout % 32 == 0, "pack_convt_weight_k222: channels must be multiples of 32");
+  return spff::pack_convt_impl(w, w_fwd, w_dgrad, cin, cout, 8, static_cast<cudaStream_t>(stream));
 }
 
 /* `s` is the INPUT (coarse) grid; y is [n, d, 2h, 2w, cout]. */
@@ -525,28 +644,8 @@ int spff_convt_k122_fwd(const void* x, long long ldx, int cin, const void* w_fwd
   int e = spff_device_check();
   if (e) return e;
   SPFF_REQUIRE(x && w_fwd && y, "convt_k122_fwd: null pointer");
-  SPFF_REQUIRE(cin % 32 == 0 && cout % 32 == 0 && cout <= 256, "convt_k122_fwd: bad channels %d -> %d", cin, cout);
-  const int KC = spff::conv3_kc(cin);
-  spff::PwParams p{};
-  p.n = s.n; p.d = s.d; p.h = s.h; p.w = s.w;
-  spff::pick_tile(s.h, s.w, 128, false, &p.bw, &p.bh);
-  p.tiles_w = (s.w + p.bw - 1) / p.bw;
-  p.tiles_h = (s.h + p.bh - 1) / p.bh;
-  p.ntiles = static_cast<long long>(s.n) * s.d * p.tiles_w * p.tiles_h;
-  p.nkc = cin / KC; p.ntap = 1; p.nquad = 4; p.N = cout;
-  p.out = static_cast<__nv_bfloat16*>(y); p.ldo = ldy; p.ho = 2 * s.h; p.wo = 2 * s.w; p.scale = 2; p.bias = bias;
-  spff::PwMaps maps;
-  e = spff::encode_grid_map(&maps.a[0], x, ldx, cin, s.n, s.d, s.h, s.w, 1, 0, 0, KC, p.bw, p.bh, KC * 2);
-  if (e) return e;
-  {
-    uint64_t dims[2] = {static_cast<uint64_t>(KC), static_cast<uint64_t>(4) * p.nkc * cout};
-    uint64_t str[1] = {static_cast<uint64_t>(KC) * 2};
-    uint32_t box[2] = {static_cast<uint32_t>(KC), static_cast<uint32_t>(cout)};
-    e = spff::encode_tmap_bf16(&maps.b, w_fwd, 2, dims, str, box, KC * 2);
-    if (e) return e;
-  }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return KC == 64 ? spff::launch_pw<64>(maps, p, st) : spff::launch_pw<32>(maps, p, st);
+  SPFF_REQUIRE(cin % 32 == 0 && cout % 32 == 0 && cin > 0 && cout > 0, "convt_k122_fwd: bad channels %d -> %d", cin, cout);
+  return spff::convt_fwd_impl(x, ldx, cin, w_fwd, bias, y, ldy, cout, s, 1, static_cast<cudaStream_t>(stream));
 }
 
 /* `s` is the coarse grid (that of dx); dy is [n, d, 2h, 2w, cout]. */
@@ -555,31 +654,8 @@ int spff_convt_k122_dgrad(const void* dy, long long lddy, int cout, const void* 
   int e = spff_device_check();
   if (e) return e;
   SPFF_REQUIRE(dy && w_dgrad && dx, "convt_k122_dgrad: null pointer");
-  SPFF_REQUIRE(cin % 32 == 0 && cout % 32 == 0 && cin <= 256, "convt_k122_dgrad: bad channels %d -> %d", cin, cout);
-  const int KC = spff::conv3_kc(cout);
-  spff::PwParams p{};
-  p.n = s.n; p.d = s.d; p.h = s.h; p.w = s.w;
-  spff::pick_tile(s.h, s.w, 128, false, &p.bw, &p.bh);
-  p.tiles_w = (s.w + p.bw - 1) / p.bw;
-  p.tiles_h = (s.h + p.bh - 1) / p.bh;
-  p.ntiles = static_cast<long long>(s.n) * s.d * p.tiles_w * p.tiles_h;
-  p.nkc = cout / KC; p.ntap = 4; p.nquad = 1; p.N = cin;
-  p.out = static_cast<__nv_bfloat16*>(dx); p.ldo = lddx; p.ho = s.h; p.wo = s.w; p.scale = 1; p.bias = nullptr;
-  spff::PwMaps maps;
-  for (int q = 0; q < 4; ++q) {
-    e = spff::encode_grid_map(&maps.a[q], dy, lddy, cout, s.n, s.d, 2 * s.h, 2 * s.w, 2, q >> 1, q & 1, KC, p.bw, p.bh,
-                              KC * 2);
-    if (e) return e;
-  }
-  {
-    uint64_t dims[2] = {static_cast<uint64_t>(KC), static_cast<uint64_t>(4) * p.nkc * cin};
-    uint64_t str[1] = {static_cast<uint64_t>(KC) * 2};
-    uint32_t box[2] = {static_cast<uint32_t>(KC), static_cast<uint32_t>(cin)};
-    e = spff::encode_tmap_bf16(&maps.b, w_dgrad, 2, dims, str, box, KC * 2);
-    if (e) return e;
-  }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return KC == 64 ? spff::launch_pw<64>(maps, p, st) : spff::launch_pw<32>(maps, p, st);
+  SPFF_REQUIRE(cin % 32 == 0 && cout % 32 == 0 && cin > 0 && cout > 0, "convt_k122_dgrad: bad channels %d -> %d", cin, cout);
+  return spff::convt_dgrad_impl(dy, lddy, cout, w_dgrad, dx, lddx, cin, s, 1, static_cast<cudaStream_t>(stream));
 }
 
 size_t spff_convt_k122_wgrad_workspace(int cin, int cout, spff_shape s) {
@@ -597,37 +673,45 @@ int spff_convt_k122_wgrad(const void* x, long long ldx, int cin, const void* dy,
   SPFF_REQUIRE(x && dy && dw && workspace, "convt_k122_wgrad: null pointer");
   SPFF_REQUIRE(cin % 64 == 0 && cout % 32 == 0, "convt_k122_wgrad: needs cin %% 64 == 0 and cout %% 32 == 0 (%d -> %d)", cin,
                cout);
-  const spff::PwWgPlan pl = spff::make_pw_plan(cin, cout, s);
-  if (workspace_bytes < pl.ws_bytes) {
-    spff::set_error("convt_k122_wgrad: workspace %zu < %zu bytes", workspace_bytes, pl.ws_bytes);
-    return SPFF_ERR_WORKSPACE;
-  }
-  SPFF_REQUIRE((pl.bw * pl.bh) % 16 == 0 && pl.bw * pl.bh * pl.cob * 2 <= 8192, "convt_k122_wgrad: cannot tile %dx%d", s.h,
-               s.w);
-  spff::PwWgParams p{};
-  p.n = s.n; p.d = s.d; p.h = s.h; p.w = s.w; p.bw = pl.bw; p.bh = pl.bh; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
-  p.ntiles = pl.ntiles; p.ncob = pl.ncob; p.ncib = pl.ncib; p.ksplit = pl.ksplit;
-  p.partial = static_cast<float*>(workspace);
-  spff::PwWgMaps maps;
-  for (int q = 0; q < 4; ++q) {
-    e = spff::encode_grid_map(&maps.dy[q], dy, lddy, cout, s.n, s.d, 2 * s.h, 2 * s.w, 2, q >> 1, q & 1, pl.cob, pl.bw,
-                              pl.bh, pl.cob * 2);
-    if (e) return e;
-  }
-  e = spff::encode_grid_map(&maps.x, x, ldx, cin, s.n, s.d, s.h, s.w, 1, 0, 0, 64, pl.bw, pl.bh, 128);
+  return spff::convt_wgrad_impl(x, ldx, cin, dy, lddy, cout, s, dw, beta, workspace, workspace_bytes, 1,
+                                static_cast<cudaStream_t>(stream));
+}
+
+/* ---- ConvTranspose3d kernel = stride = (2,2,2) (Cicek3DUNet up4..up1, models.py:733-739) -------------------
+ * `s` is the coarse grid; the fine tensors are [n, 2d, 2h, 2w, c]. Weight [cin][cout][2][2][2]. */
+int spff_convt_k222_fwd(const void* x, long long ldx, int cin, const void* w_fwd, const float* bias, void* y,
+                        long long ldy, int cout, spff_shape s, void* stream) {
+  int e = spff_device_check();
   if (e) return e;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int ctas = pl.ncob * pl.ncib * pl.ksplit;
-  if (pl.cob == 64 && pl.cib == 128) e = spff::launch_pw_wgrad<64, 128>(maps, p, ctas, st);
-  else if (pl.cob == 64) e = spff::launch_pw_wgrad<64, 64>(maps, p, ctas, st);
-  else if (pl.cib == 128) e = spff::launch_pw_wgrad<32, 128>(maps, p, ctas, st);
-  else e = spff::launch_pw_wgrad<32, 64>(maps, p, ctas, st);
+  SPFF_REQUIRE(x && w_fwd && y, "convt_k222_fwd: null pointer");
+  SPFF_REQUIRE(cin % 32 == 0 && cout % 32 == 0 && cin > 0 && cout > 0, "convt_k222_fwd: bad channels %d -> %d", cin, cout);
+  return spff::convt_fwd_impl(x, ldx, cin, w_fwd, bias, y, ldy, cout, s, 2, static_cast<cudaStream_t>(stream));
+}
+
+int spff_convt_k222_dgrad(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
+                          int cin, spff_shape s, void* stream) {
+  int e = spff_device_check();
   if (e) return e;
-  const long long total = 4LL * cin * cout;
-  spff::pw_wgrad_reduce_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(p.partial, dw, cin, cout, pl.cob,
-                                                                                      pl.cib, pl.ksplit, beta);
-  SPFF_CUDA(cudaGetLastError());
-  return 0;
+  SPFF_REQUIRE(dy && w_dgrad && dx, "convt_k222_dgrad: null pointer");
+  SPFF_REQUIRE(cin % 32 == 0 && cout % 32 == 0 && cin > 0 && cout > 0, "convt_k222_dgrad: bad channels %d -> %d", cin, cout);
+  return spff::convt_dgrad_impl(dy, lddy, cout, w_dgrad, dx, lddx, cin, s, 2, static_cast<cudaStream_t>(stream));
+}
+
+size_t spff_convt_k222_wgrad_workspace(int cin, int cout, spff_shape s) {
+  return spff_convt_k122_wgrad_workspace(cin, cout, s);
+}
+
+/* dw[cin][cout][2][2][2] (fp32) = beta*dw + gradient: the four-quadrant contraction once per depth tap. */
+int spff_convt_k222_wgrad(const void* x, long long ldx, int cin, const void* dy, long long lddy, int cout,
+                          spff_shape s, float* dw, float beta, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  int e = spff_device_check();
+  if (e) return e;
+  SPFF_REQUIRE(x && dy && dw && workspace, "convt_k222_wgrad: null pointer");
+  SPFF_REQUIRE(cin % 64 == 0 && cout % 32 == 0, "convt_k222_wgrad: needs cin %% 64 == 0 and cout %% 32 == 0 (%d -> %d)", cin,
+               cout);
+  return spff::convt_wgrad_impl(x, ldx, cin, dy, lddy, cout, s, dw, beta, workspace, workspace_bytes, 2,
+                                static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -313,3 +313,81 @@ def head_loss_fused(x, w, b, labels, ignore_index, n_valid, gscale, acc, counts,
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     call("spff_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
          int(step), float(grad_scale), stream_ptr())
+
+
+# ------------------------------------------------------------------------------------------------
+# "3DUNet" control (Cicek3DUNet): (2,2,2) transposed conv / pool, BatchNorm, depth resampling, SGD
+# ------------------------------------------------------------------------------------------------
+def pack_convt_weight_k222(w):
+    """nn.ConvTranspose3d weight [Cin,Cout,2,2,2] fp32 -> (w_fwd, w_dgrad) bf16."""
+    cin, cout = w.shape[0], w.shape[1]
+    w = w.detach().contiguous().float()
+    wf = torch.empty(8 * cin * cout, dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty(8 * cin * cout, dtype=torch.bfloat16, device=w.device)
+    call("spff_pack_convt_weight_k222", ptr(w), ptr(wf), ptr(wd), cin, cout, stream_ptr())
+    return wf, wd
+
+
+def convt_k222_fwd(x, cin, w_fwd, bias, y, cout):
+    s, ldx = _view(x, cin)
+    s2, ldy = _view(y, cout)
+    assert (s2.d, s2.h, s2.w) == (2 * s.d, 2 * s.h, 2 * s.w)
+    call("spff_convt_k222_fwd", ptr(x), ldx, cin, ptr(w_fwd), ptr(bias), ptr(y), ldy, cout, s, stream_ptr())
+
+
+def convt_k222_dgrad(dy, cout, w_dgrad, dx, cin):
+    s, lddx = _view(dx, cin)
+    s2, lddy = _view(dy, cout)
+    assert (s2.d, s2.h, s2.w) == (2 * s.d, 2 * s.h, 2 * s.w)
+    call("spff_convt_k222_dgrad", ptr(dy), lddy, cout, ptr(w_dgrad), ptr(dx), lddx, cin, s, stream_ptr())
+
+
+def convt_k222_wgrad(x, cin, dy, cout, dw, beta=0.0):
+    s, ldx = _view(x, cin)
+    _, lddy = _view(dy, cout)
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == (cin, cout, 2, 2, 2)
+    ws = workspace(int(_lib.lib.spff_convt_k222_wgrad_workspace(cin, cout, s)), x.device)
+    call("spff_convt_k222_wgrad", ptr(x), ldx, cin, ptr(dy), lddy, cout, s, ptr(dw), float(beta), ptr(ws), ws.numel(),
+         stream_ptr())
+
+
+def depth_resample(x, y, matrix):
+    """y[n, do, ...] = sum_di matrix[do, di] * x[n, di, ...] for contiguous x [n, din, *inner], y [n, dout, *inner]
+    (bf16 or fp32); matrix: CUDA fp32 [dout, din]."""
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == y.dtype and x.dtype in (torch.bfloat16, torch.float32)
+    n, din = x.shape[0], x.shape[1]
+    dout = y.shape[1]
+    inner = x[0, 0].numel()
+    assert y.shape[0] == n and y[0, 0].numel() == inner and tuple(matrix.shape) == (dout, din)
+    assert matrix.dtype == torch.float32 and matrix.is_contiguous() and matrix.is_cuda
+    call("spff_depth_resample", ptr(x), ptr(y), x.element_size(), n, din, dout, inner, ptr(matrix), stream_ptr())
+
+
+def bn_coeffs(gamma, beta, eps, n, c, count, coef, partial=None, slots=0, stats=None, momentum=0.1, running_mean=None,
+              running_var=None, eval_mode=False):
+    ws = workspace(int(_lib.lib.spff_bn_coeffs_workspace(c)), coef.device)
+    call("spff_bn_coeffs", ptr(partial), int(slots), ptr(stats), ptr(gamma), ptr(beta), float(eps), n, c, int(count),
+         float(momentum), ptr(running_mean), ptr(running_var), int(eval_mode), ptr(coef), ptr(ws), ws.numel(), stream_ptr())
+
+
+def bn_bwd_coeffs(R, coef, gamma, c, shape, bcoef, dgamma, dbeta):
+    call("spff_bn_bwd_coeffs", ptr(R), ptr(coef), ptr(gamma), c, shape, ptr(bcoef), ptr(dgamma), ptr(dbeta), stream_ptr())
+
+
+def maxpool222_fwd(y, ypool, c):
+    s, ldy = _view(y, c)
+    s2, ldp = _view(ypool, c)
+    assert (s2.d, s2.h, s2.w) == (s.d // 2, s.h // 2, s.w // 2)
+    call("spff_maxpool222_fwd", ptr(y), ldy, ptr(ypool), ldp, c, s, stream_ptr())
+
+
+def maxpool222_bwd_add(dpool, y, dskip, c, accumulate):
+    s, ldy = _view(y, c)
+    _, ldp = _view(dpool, c)
+    _, ldd = _view(dskip, c)
+    call("spff_maxpool222_bwd_add", ptr(dpool), ldp, ptr(y), ldy, ptr(dskip), ldd, c, s, int(accumulate), stream_ptr())
+
+
+def sgd_step(p, g, buf, lr, momentum, weight_decay, nesterov, first_step, grad_scale=1.0):
+    call("spff_sgd_step", ptr(p), ptr(g), ptr(buf), p.numel(), float(lr), float(momentum), float(weight_decay),
+         int(bool(nesterov)), int(bool(first_step)), float(grad_scale), stream_ptr())
