@@ -100,5 +100,18 @@ _add_variant("PlainCore_UNet",
              build_class("LitSPCT_ControlUNet", **{**_SPCT_COMMON, "use_se": False, "use_specse": False}),
              MultiDicomDataModule3D, CHECKPOINT_DIR / "PlainCore_UNet")            # config.py:460-476
 
+
+
+def make_cicek_depth_adapter_sgd_wce():
+    """config.py:283-303: Cicek 3D U-Net + depth adapter, SGD like the paper, plain softmax CE."""
+    from innovative3D.models import LitCicek3DUNet_DepthAdapter_Published
+    return LitCicek3DUNet_DepthAdapter_Published(
+        num_classes=NUM_CLASSES, lr=1e-2, momentum=0.99, nesterov=False, weight_decay=0.0, ignore_index=255,
+        class_weights=None, voxel_weight_key=None, ce_weight=1.0, dice_weight=0.0, use_bn=True, target_depth=16,
+        include_bg_in_dice=False)
+
+
+_add_variant("3DUNet", make_cicek_depth_adapter_sgd_wce, MultiDicomDataModule3D, CHECKPOINT_DIR / "3DUNet")   # config.py:306-311
+
 VARIANT_NAMES = [v[0] for v in VARIANTS]
 SELECTED_VARIANT = os.getenv("INNOVATIVE3D_VARIANT")

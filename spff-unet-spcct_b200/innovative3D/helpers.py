@@ -91,6 +91,17 @@ class _CrossEntropyFn(torch.autograd.Function):
         return dl.view_as(logits).to(logits.dtype), None, None, None
 
 
+def masked_ce_loss(logits, labels, ignore_index=255):
+    """Sum of the valid voxels' nll over max(#valid, 1): `_weighted_softmax_ce` of the Cicek wrapper with
+    class_weights None and no voxel weights (models.py:779-798). Shares the tally pass with the metrics."""
+    ign = _NO_IGNORE if ignore_index is None else int(ignore_index)
+    t = _tally(logits, labels, ign)
+    if getattr(t, "_clamped", None) is None:
+        t._clamped = LossTally(t.k, t.nll.device)
+        t._clamped.nll, t._clamped.count, t._clamped.confusion = t.nll, t.count.clamp(min=1), t.confusion
+    return _CrossEntropyFn.apply(logits, labels, ign, t._clamped)
+
+
 def _dice_from_tally(t: LossTally, smooth: float) -> torch.Tensor:
     cm = t.confusion.double()
     tp = cm.diagonal()[1:]

@@ -650,3 +650,272 @@ class LitSPCT_ControlUNet(BaseLitModel):
         super().__init__(num_classes=num_classes, lr=lr, is_3d=True, **kw)
         self.model = UNet3D_SpectralCore(in_channels=1, num_classes=num_classes, base=base, ksd=ksd, use_se=use_se,
                                          use_specse=use_specse, use_spatial=use_spatial, use_skip_gate=use_skip_gate)
+
+
+# --------------------------------------------------------------------------------------------------
+# "3DUNet" control: Cicek 3D U-Net behind a depth adapter (models.py:153-163, 718-846; config.py:283-311)
+# --------------------------------------------------------------------------------------------------
+def _resize_depth_like(x: torch.Tensor, target_depth: int):
+    """[B,C,D,H,W] -> D resized to target_depth by the trilinear rule (models.py:153-157), as a plane-mixing
+    matrix on the device (spff_depth_resample). Used by callers outside the fused path."""
+    B, C, D, H, W = x.shape
+    if D == target_depth:
+        return x
+    from spff_b200.cicek import depth_matrix
+    if not x.is_cuda:
+        raise RuntimeError("_resize_depth_like (B200 build) needs a CUDA tensor; there is no CPU fallback")
+    xin = x.float().contiguous().view(B * C, D, H * W)
+    if (H * W) % 4:
+        raise ValueError("H*W must be a multiple of 4")
+    out = torch.empty(B * C, target_depth, H * W, device=x.device)
+    ops.depth_resample(xin, out, depth_matrix(D, target_depth).to(x.device))
+    return out.view(B, C, target_depth, H, W)
+
+
+_resize_logits_depth_like = _resize_depth_like
+
+
+class _CicekFn(torch.autograd.Function):
+    """Cicek3DUNet (+ depth adapter) as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, x, net, target_depth, *params):
+        logits, state = net.engine.forward_saved(x, target_depth, training=net.training)
+        ctx.net, ctx.state = net, state
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        net = ctx.net
+        flat = torch.zeros(net._flat_numel, device=dlogits.device)
+        G = net._views(flat)
+        net.engine.backward_saved(ctx.state, dlogits, G)
+        ctx.state = None
+        return (None, None, None) + tuple(G[n] for n in net._names)
+
+
+class Cicek3DUNet(nn.Module):
+    """Çiçek et al. 3-D U-Net (models.py:718-751): five levels of (3x3x3 conv, BatchNorm3d, ReLU) x 2,
+    MaxPool3d(2), ConvTranspose3d(2, stride 2), cat([up, skip]), 1x1x1 head; base 32 -> 512 channels at the
+    bottleneck. Same constructor, attribute names and construction order as the reference (so the same seed
+    draws the same weights and checkpoints interchange); the sub-modules are parameter containers and the graph
+    runs in `spff_b200.cicek.CicekEngine`. D, H, W must be multiples of 16."""
+
+    def __init__(self, num_classes: int, base: int = 32, use_bn: bool = True):
+        super().__init__()
+        if not use_bn:
+            raise NotImplementedError("the B200 path implements the BatchNorm configuration the variant uses "
+                                      "(use_bn=True, config.py:299)")
+        if int(base) != 32:
+            raise NotImplementedError("the B200 kernels are built for base=32 (models.py:767)")
+        if not 0 < num_classes <= 16:
+            raise NotImplementedError("the head / loss kernels support up to 16 classes")
+
+        def block(ci, co):
+            return nn.Sequential(nn.Conv3d(ci, co, 3, padding=1, bias=False), nn.BatchNorm3d(co), nn.ReLU(inplace=True),
+                                 nn.Conv3d(co, co, 3, padding=1, bias=False), nn.BatchNorm3d(co), nn.ReLU(inplace=True))
+
+        self.enc1 = block(1, base); self.pool1 = nn.MaxPool3d(2)
+        self.enc2 = block(base, base * 2); self.pool2 = nn.MaxPool3d(2)
+        self.enc3 = block(base * 2, base * 4); self.pool3 = nn.MaxPool3d(2)
+        self.enc4 = block(base * 4, base * 8); self.pool4 = nn.MaxPool3d(2)
+        self.bott = block(base * 8, base * 16)
+        self.up4 = nn.ConvTranspose3d(base * 16, base * 8, 2, stride=2)
+        self.dec4 = block(base * 8 + base * 8, base * 8)
+        self.up3 = nn.ConvTranspose3d(base * 8, base * 4, 2, stride=2)
+        self.dec3 = block(base * 4 + base * 4, base * 4)
+        self.up2 = nn.ConvTranspose3d(base * 4, base * 2, 2, stride=2)
+        self.dec2 = block(base * 2 + base * 2, base * 2)
+        self.up1 = nn.ConvTranspose3d(base * 2, base, 2, stride=2)
+        self.dec1 = block(base + base, base)
+        self.out = nn.Conv3d(base, num_classes, 1)
+        self._num_classes, self._base = int(num_classes), int(base)
+        self._engine = None
+        self._flat: Optional[torch.Tensor] = None
+        self._names: List[str] = []
+        self._slots: Dict[str, tuple] = {}
+        self._flat_numel = 0
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            from spff_b200.cicek import CicekEngine
+            self._engine = CicekEngine(self._num_classes, self._base, lambda: self._param_data, lambda: self._buffer_data,
+                                       lambda: tuple(p._version for p in self._param_objs.values()))
+        return self._engine
+
+    def _views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return {n: flat[o:o + k].view(shape) for n, (o, k, shape) in self._slots.items()}
+
+    def materialize(self):
+        """(Re)build the flat fp32 parameter buffer: every parameter's `.data` becomes a view of it, so the gradient
+        all-reduce and the fused SGD run over one contiguous range. BatchNorm buffers stay where they are."""
+        from spff_b200.cicek import flat_names
+        dev = self.out.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("Cicek3DUNet (B200 build) must live on a CUDA sm_100 device: there is no CPU fallback. "
+                               "Call .to('cuda') / .cuda() first.")
+        named = list(self.named_parameters())
+        ok = self._flat is not None and self._flat.device == dev
+        if ok:
+            base, end = self._flat.data_ptr(), self._flat.data_ptr() + 4 * self._flat_numel
+            ok = all(base <= p.data_ptr() < end and p.dtype == torch.float32 for _, p in named)
+        if not ok:
+            slots, total = flat_names(named)
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            for n, p in named:
+                o, k, shape = slots[n]
+                v = flat[o:o + k].view(shape)
+                v.copy_(p.data)
+                p.data = v
+            self._flat, self._slots, self._flat_numel = flat, slots, total
+            self._names = [n for n, _ in named]
+            self._param_objs = dict(named)
+            self._param_data = {n: p.data for n, p in named}
+            if self._engine is not None:
+                self._engine.invalidate_weights()
+        self._buffer_data = dict(self.named_buffers())   # .to() / load_state_dict may have replaced them
+
+    def _run(self, x, target_depth: Optional[int]):
+        x = _pick_first_if_seq(x)
+        if x.ndim == 4:
+            x = x.unsqueeze(1)
+        self.materialize()
+        x = x.to(self.out.weight.device)
+        params = [self._param_objs[n] for n in self._names]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _CicekFn.apply(x, self, target_depth, *params)
+        return self.engine.infer(x, target_depth, training=self.training)
+
+    def forward(self, x):
+        """logits [B,K,D,H,W] of x [B,1,D,H,W] (D, H, W multiples of 16)."""
+        return self._run(x, None)
+
+    def forward_adapted(self, x, target_depth: int):
+        """resize D -> target_depth, the network, resize back — fused (no 16-plane logits in memory)."""
+        return self._run(x, int(target_depth))
+
+
+class LitCicek3DUNet_DepthAdapter_Published(pl.LightningModule):
+    """"3DUNet" (models.py:753-846 as configured by config.py:283-303): trilinear depth adapter 5 -> 16 -> 5 around
+    Cicek3DUNet, plain CE over valid voxels, SGD(lr 1e-2, momentum 0.99). Same constructor as the reference; the
+    options its configuration leaves off (class / voxel weights, the soft Dice term, use_bn=False) raise."""
+
+    def __init__(self, num_classes: int, target_depth: int = 16, lr: float = 1e-2, momentum: float = 0.99,
+                 nesterov: bool = False, weight_decay: float = 0.0, ignore_index: Optional[int] = 255,
+                 class_weights: Optional[list] = None, voxel_weight_key: Optional[str] = None, ce_weight: float = 1.0,
+                 dice_weight: float = 0.0, use_bn: bool = True, include_bg_in_dice: bool = False, *args, **kwargs):
+        super().__init__()
+        self.save_hyperparameters(dict(num_classes=num_classes, target_depth=target_depth, lr=lr, momentum=momentum,
+                                       nesterov=nesterov, weight_decay=weight_decay, ignore_index=ignore_index,
+                                       class_weights=class_weights, voxel_weight_key=voxel_weight_key, ce_weight=ce_weight,
+                                       dice_weight=dice_weight, use_bn=use_bn, include_bg_in_dice=include_bg_in_dice))
+        if class_weights is not None or voxel_weight_key is not None:
+            raise NotImplementedError("class / voxel weighted CE is off in the 3DUNet variant (config.py:293-294)")
+        if float(dice_weight) > 0.0:
+            raise NotImplementedError("the soft Dice term is off in the 3DUNet variant (dice_weight=0, config.py:297)")
+        self.backbone = Cicek3DUNet(num_classes=num_classes, base=32, use_bn=use_bn)
+        self.target_depth = int(target_depth)
+        self.class_weights = None
+        self.voxel_weight_key = None
+        self.ignore_index = ignore_index
+        self.include_bg_in_dice = include_bg_in_dice
+        self.ce_weight, self.dice_weight = float(ce_weight), float(dice_weight)
+        self._fused = None
+
+    @property
+    def model(self):
+        """`.model` is what the callers' profilers read (train.py:1416); for this wrapper it is the backbone."""
+        return self.backbone
+
+    def forward(self, x):
+        return self.backbone.forward_adapted(x, self.target_depth)
+
+    def _weighted_softmax_ce(self, logits, target, voxel_weights=None):
+        from .helpers import masked_ce_loss
+        if voxel_weights is not None:
+            raise NotImplementedError("voxel weights are off in the 3DUNet variant")
+        if target.ndim == 5 and target.shape[1] == 1:
+            target = target[:, 0]
+        return masked_ce_loss(logits, target, self.ignore_index)
+
+    def _loss_and_log(self, logits, y, stage: str, voxel_w=None, log_metrics: bool = True):
+        y = _canonicalize_targets_3d(y).to(logits.device)
+        loss = self._weighted_softmax_ce(logits, y, voxel_w) * self.ce_weight
+        self.log(f"{stage}_loss", loss, prog_bar=(stage == "train"), on_step=False, on_epoch=True, sync_dist=True)
+        if log_metrics:
+            macro_dice = per_class_metrics_3d(logits, y, self.hparams.num_classes, ignore_index=self.ignore_index)[3]
+            self.log(f"{stage}_macro_dice", macro_dice, on_step=False, on_epoch=True, prog_bar=True, sync_dist=True)
+        return loss
+
+    def _unpack(self, batch):
+        if isinstance(batch, (list, tuple)):
+            x, y = batch
+            return x, y, None
+        return batch["image"], batch["label"], None
+
+    def training_step(self, batch, _):
+        x, y, vw = self._unpack(batch)
+        return self._loss_and_log(self(x), y, "train", voxel_w=vw)
+
+    def validation_step(self, batch, _):
+        x, y, vw = self._unpack(batch)
+        return self._loss_and_log(self(x), y, "val", voxel_w=vw, log_metrics=True)
+
+    def test_step(self, batch, _):
+        x, y, vw = self._unpack(batch)
+        return self._loss_and_log(self(x), y, "test", voxel_w=vw)
+
+    def configure_optimizers(self):
+        return torch.optim.SGD(self.parameters(), lr=self.hparams.lr, momentum=self.hparams.momentum,
+                               nesterov=bool(self.hparams.nesterov), weight_decay=self.hparams.weight_decay)
+
+    # -- B200-native fused training step ---------------------------------------------------------
+    def fit_step(self, batch, optimize: bool = True):
+        """forward + CE + backward (+ data-parallel gradient all-reduce + SGD step) without materialising logits:
+        `loss = training_step(batch); loss.backward(); optimizer.step()` of the reference with
+        torch.optim.SGD(lr, momentum, nesterov, weight_decay). BatchNorm runs in training mode over the whole
+        (per-rank) batch. Returns {"loss": device scalar, "tally": LossTally}; nothing synchronises the host."""
+        x, y, _ = self._unpack(batch)
+        x, y = _pick_first_if_seq(x), _pick_first_if_seq(y)
+        net = self.backbone
+        if x.ndim == 4:
+            x = x.unsqueeze(1)
+        net.materialize()
+        dev = net._flat.device
+        y = _canonicalize_targets_3d(y) if y.dtype not in (torch.uint8, torch.int64) or y.ndim != 4 else y
+        x = x.to(dev, non_blocking=True)
+        y = y.to(dev, non_blocking=True)
+        st = self._fused
+        if st is None or st["flat"] is not net._flat:
+            st = self._fused = dict(flat=net._flat, grad=torch.zeros_like(net._flat), buf=torch.zeros_like(net._flat),
+                                    step=0, tally=LossTally(self.hparams.num_classes, dev))
+            st["G"] = net._views(st["grad"])
+        st["grad"].zero_()
+        st["tally"].zero()
+        ign = -1 if self.ignore_index is None else int(self.ignore_index)
+        with torch.no_grad():
+            net.engine.train_step(x, y, st["G"], st["tally"], self.target_depth, ignore_index=ign)
+            gscale = dp.allreduce_grads(st["grad"])
+            if optimize:
+                ops.sgd_step(net._flat, st["grad"], st["buf"], float(self.hparams.lr), float(self.hparams.momentum),
+                             float(self.hparams.weight_decay), bool(self.hparams.nesterov), st["step"] == 0,
+                             gscale * self.ce_weight)
+                st["step"] += 1
+                net.engine.invalidate_weights()
+            t = st["tally"]
+            loss = (self.ce_weight * t.nll[0] / t.count[0].clamp(min=1).double()).float()
+        return {"loss": loss, "tally": t}
+
+    def fused_grads(self) -> Dict[str, torch.Tensor]:
+        return self._fused["G"]
+
+    @torch.no_grad()
+    def predict_labels(self, x) -> torch.Tensor:
+        """uint8 label map [B,D,H,W] (argmax fused into the head kernel); BatchNorm as the module's mode says."""
+        x = _pick_first_if_seq(x)
+        if x.ndim == 4:
+            x = x.unsqueeze(1)
+        net = self.backbone
+        net.materialize()
+        return net.engine.infer(x.to(net._flat.device), self.target_depth, training=net.training, argmax=True)

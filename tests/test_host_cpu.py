@@ -46,12 +46,15 @@ def test_no_gpu_is_an_error_not_a_fallback():
 def test_variants_registry_surface():
     from innovative3D import config as C
     names = [v[0] for v in C.VARIANTS]
-    assert names[:1] == ["SPFF-UNet"] and {"E_SP_UNet", "FG_SP_UNet", "SP_UNet", "PlainCore_UNet"} <= set(names)
+    assert names[:1] == ["SPFF-UNet"] and {"E_SP_UNet", "FG_SP_UNet", "SP_UNet", "PlainCore_UNet", "3DUNet"} <= set(names)
     assert (C.NUM_CLASSES, C.NUM_FRAMES, C.IGNORE_INDEX, C.BATCH_SIZE, C.BEST_LR, C.SEEDS) == (13, 5, 255, 1, 1e-4, [42, 123, 999])
     for name, builder, dm, ckpt in C.VARIANTS:
         lit = builder()
         assert hasattr(lit, "model") and lit.hparams.num_classes == 13 and callable(dm)
         opt = lit.configure_optimizers()
+        if name == "3DUNet":     # SGD like the paper (config.py:287-290, models.py:844-846)
+            assert isinstance(opt, torch.optim.SGD) and opt.defaults["momentum"] == 0.99 and opt.defaults["lr"] == 1e-2
+            continue
         assert isinstance(opt["optimizer"], torch.optim.Adam) and opt["lr_scheduler"]["monitor"] == "val_macro_dice"
 
 
