@@ -105,7 +105,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus: int):
+def workload_config(n_gpus: int, variant: str = "SPFF-UNet", samples: int = SAMPLES):
+    if variant != "SPFF-UNet":   # BASELINE.json configs[3]: the ablation controls through the same kernels
+        opt = "SGD(momentum)" if variant == "3DUNet" else "Adam"
+        return {
+            "workload": f"{variant} bf16 training step (control, BASELINE.json configs[3]), synthetic x[{samples},1,{FRAMES},{H},{W}] per GPU"
+                        + (" (16 planes inside the depth adapter; whole batch resident: BatchNorm)" if variant == "3DUNet" else ""),
+            "samples_per_gpu": samples, "voxels_per_gpu_step": samples * FRAMES * H * W, "num_classes": NUM_CLASSES,
+            "step": f"fwd + loss + bwd + grad all-reduce + {opt}", "parallelism": f"dp{n_gpus}",
+            "l2": "working set >> 126 MB L2 (inputs larger than L2; no flush needed)",
+        }
     return {
         "workload": f"SPFF-UNet bf16 training step, synthetic batch 8x5x128^3 per GPU = x[{SAMPLES},1,{FRAMES},{H},{W}] "
                     f"(BASELINE.json configs[1]; configs[2] for N>1)",
@@ -186,9 +195,12 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    samples = int(os.environ.get("SPFF_BENCH_SAMPLES", SAMPLES))
+    variant = args.variant
+    samples = int(os.environ.get("SPFF_BENCH_SAMPLES", 256 if variant == "3DUNet" else SAMPLES))
     torch.manual_seed(42)
-    lit = dict((v[0], v[1]) for v in C.VARIANTS)["SPFF-UNet"]().to(dev)
+    lit = dict((v[0], v[1]) for v in C.VARIANTS)[variant]().to(dev)
+    if variant == "3DUNet":
+        lit.train()
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.randn(samples, 1, FRAMES, H, W, generator=g).pin_memory()
     lab_host = torch.randint(0, NUM_CLASSES, (samples, FRAMES, H, W), generator=g).pin_memory()
@@ -260,10 +272,11 @@ def run_b200(args):
         value = world * vox * args.steps / sec
         total_ms = sum(v[1] for v in brk.values())
         line = {
-            "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if variant == "SPFF-UNet" else f"{variant} train voxels/s", "value": value, "unit": "voxels/s",
+            "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, variant, samples),
             "clocks": clk,
             "e2e": {"value": world * vox * args.steps / sec_e2e, "unit": "voxels/s",
                     "h2d_bytes_per_step": x_host.numel() * 4 + lab_host.numel() * 8, "d2h_bytes_per_step": 4,
@@ -275,12 +288,13 @@ def run_b200(args):
                          "launches": n_f + n_d, "ms_per_step": (ms_f + ms_d) / args.steps,
                          "wgrad": {"achieved": fl_w / max(ms_w, 1e-9) * 1e3 / 1e12, "ms_per_step": ms_w / args.steps,
                                    "launches": n_w},
-                         "step_tensor_frac": value / world * FLOP_PER_VOXEL_TRAIN / 1e12 / peak},
+                         "step_tensor_frac": (value / world * FLOP_PER_VOXEL_TRAIN / 1e12 / peak if variant != "3DUNet" else
+                                              (fl_f + fl_d + fl_w) / sec * 1e-12 / peak)},
             "breakdown_ms": {k: round(v[1], 3) for k, v in sorted(brk.items(), key=lambda kv: -kv[1][1])},
             "breakdown_total_ms": round(total_ms, 3),
             "final_loss": final_loss,
         }
-        if not args.no_cpu and world >= 1:
+        if not args.no_cpu and world >= 1 and variant == "SPFF-UNet":
             t0 = time.perf_counter()
             cs = 8
             times, threads = cpu_step_time(cs, reps=4, warmup=1, budget_s=25.0)
@@ -302,6 +316,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--variant", default="SPFF-UNet",
+                    choices=["SPFF-UNet", "E_SP_UNet", "FG_SP_UNet", "SP_UNet", "PlainCore_UNet", "3DUNet"],
+                    help="SPFF-UNet is the headline (BASELINE.json configs[1]); the others are the controls of configs[3]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
