@@ -124,6 +124,20 @@ def workload_config(n_gpus: int, variant: str = "SPFF-UNet", samples: int = SAMP
     }
 
 
+def conv_traffic():
+    """Mean DRAM bytes (read + write) per conv3_fprop_kernel launch from the committed ncu capture
+    (profiles/r01f_conv_traffic.json: every conv launch of `SPFF_BENCH_SAMPLES=256 bench.py`, i.e. the same 256-slice
+    launches as the default sample group). None when the capture is absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01f_conv_traffic.json")) as f:
+            k = json.load(f)["kernels"]
+        rows = [v for name, v in k.items() if "conv3_fprop_kernel" in name]
+        n = sum(v["launches"] for v in rows)
+        return sum(v["launches"] * (v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"]) for v in rows) / n
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------------
 # clocks
 # --------------------------------------------------------------------------------------------------
@@ -283,7 +297,10 @@ def run_b200(args):
                     "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "conv3_fprop_kernel (3x3x3 conv forward + dgrad launches)",
-                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "traffic": conv_traffic() if variant == "SPFF-UNet" else None,
+                         "traffic_note": "mean DRAM bytes per launch over all conv3_fprop launches (ncu, 256-slice sample group); "
+                                         "algorithmic (activations in + out, bf16): 1.426e9 B per launch",
                          "peak_kind": f"{peak_kind} sustained bf16 (kernel timed inside a long step)",
                          "launches": n_f + n_d, "ms_per_step": (ms_f + ms_d) / args.steps,
                          "wgrad": {"achieved": fl_w / max(ms_w, 1e-9) * 1e3 / 1e12, "ms_per_step": ms_w / args.steps,
