@@ -152,8 +152,12 @@ int spff_gate_micro_fwd(const float* S, const float* g1, const float* bt, const 
  * plain != 0: only slots 2 and 4 are produced (all that spff_gate_micro_bwd(flags = 0) reads).
  * workspace as for spff_norm_act_reduce: fixed-order overwrite of the produced slots, or NULL for atomics (+=). */
 size_t spff_norm_act_bwd_reduce_workspace(int c, spff_shape s, int plain);
+/* S (may be NULL): the forward statistic S[n][d][c] = sum_{h,w} lrelu(x*A + B) of the same tensor
+ * (spff_norm_act_reduce). With a workspace and (plain or S given) a leaner first stage runs: the two xhat sums
+ * follow from the others, sum dout*m*xhat = (sum dout*a - beta*sum dout*m)/gamma and
+ * sum m*xhat = (S - beta*sum m)/gamma (gamma == 0: those two read 0). */
 int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
-                             float* R, int c, spff_shape s, float slope, int plain, void* workspace,
+                             float* R, const float* S, int c, spff_shape s, float slope, int plain, void* workspace,
                              size_t workspace_bytes, void* stream);
 /* Backward micro-kernel: consumes R (and S), recomputes the gates, produces
  *   bcoef[n][c] = {gamma*rstd, mean(dz), mean(dz*xhat), 0}, dSa[n][d][c], Pout[n][d][c]

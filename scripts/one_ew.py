@@ -11,6 +11,10 @@ c = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 d = 5
 dev = "cuda"
+from spff_b200 import _lib
+for key, env in ((3, "EW_GRID4"), (4, "EW_GRID8")):
+    if os.getenv(env):
+        _lib.lib.spff_debug_set(key, int(os.environ[env]))
 bf = lambda *s: torch.randn(*s, device=dev).to(torch.bfloat16)
 x = bf(n, d, h, h, c); dout = bf(n, d, h, h, c); y = torch.empty_like(x); dx = torch.empty_like(x)
 cat = bf(n, d, h, h, 2 * c)
@@ -35,6 +39,10 @@ cases = [
     ("affine_apply+pool", 2.25 * el, lambda: ops.norm_act_affine_apply(x, coef, P, Q, cat[..., c:], yp, c, 0.01)),
     ("bwd_reduce", 2 * el, lambda: ops.norm_act_bwd_reduce(dout, x, coef, R, c, 0.01)),
     ("bwd_reduce_plain", 2 * el, lambda: ops.norm_act_bwd_reduce(dout, x, coef, R, c, 0.01, plain=True)),
+    ("bwd_reduce_fixed_lean", 2 * el, lambda: ops.norm_act_bwd_reduce(dout, x, coef, R, c, 0.01, fixed_order=True, S=S)),
+    ("bwd_reduce_fixed_old", 2 * el, lambda: ops.norm_act_bwd_reduce(dout, x, coef, R, c, 0.01, fixed_order=True)),
+    ("bwd_reduce_plain_fixed_lean", 2 * el, lambda: ops.norm_act_bwd_reduce(dout, x, coef, R, c, 0.01, plain=True, fixed_order=True)),
+    ("norm_act_reduce_fixed", el, lambda: ops.norm_act_reduce(x, coef, S, c, 0.01, fixed_order=True)),
     ("bwd_apply", 3 * el, lambda: ops.norm_act_bwd_apply(dout, x, coef, bcoef, P, Q, dx, c, 0.01)),
     ("maxpool_bwd_add", 3.25 * el, lambda: ops.maxpool_bwd_add(dpool, cat[..., c:], cat[..., :c], c, True)),
 ]

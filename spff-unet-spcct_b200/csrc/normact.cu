@@ -685,6 +685,124 @@ norm_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long ld
   }
 }
 
+// Leaner first stage for the fixed-order path. With a = lrelu(z) = m*z and xhat = (z - beta)/gamma the two xhat sums
+// of R follow from sums the kernel needs anyway:
+//   sum dout*m*xhat = (sum dout*m*z - beta * sum dout*m) / gamma        (slot 4 from slots 0 and 2)
+//   sum m*xhat      = (S - beta * sum m) / gamma,  S = sum a = sum m*z   (slot 5 from the forward statistic S and slot 3)
+// so only {dout*m*z, dout, dout*m, m} (PLAIN: {dout*m, dout*m*z}) are accumulated, with the per-channel state
+// reduced to (A, B): about half the instructions per element of norm_act_bwd_reduce4_kernel, which was
+// issue-bound (ncu: sm throughput 71-74 %, DRAM 44-58 %). sum_chunks_bwd_kernel folds the chunks in a fixed order
+// and applies the two identities. Raw partial layout: part[plane][chunk][c][NKR], NKR = 2 (PLAIN) or 4.
+template <bool PLAIN>
+__global__ void __launch_bounds__(kBlock, PLAIN ? 5 : 4)
+norm_act_bwd_reduce4v2_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ x,
+                              long long ldx, const float* __restrict__ coef, PlaneGrid4 g, int d, int c, float slope,
+                              float* __restrict__ part) {
+  extern __shared__ float red[];
+  constexpr int NKR = PLAIN ? 2 : 4;
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.cv, r = threadIdx.x / g.cv;
+  const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  float A[4], B[4];
+  {
+    const float4* cf = reinterpret_cast<const float4*>(coef) + static_cast<long long>(n) * c + v * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(cf + i);
+      A[i] = t.x; B[i] = t.y;
+    }
+  }
+  float acc[NKR][4];
+#pragma unroll
+  for (int k = 0; k < NKR; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
+  constexpr int U = 4;
+  int dead = 0;   // rows past the chunk that ran through the arithmetic with x = dout = 0
+  for (int p = p0 + r; p < p1; p += U * g.rpi) {
+    uint2 rx[U], rg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = p + u * g.rpi < p1;
+      rx[u] = ok ? ldg8(x + (base + p + u * g.rpi) * ldx + v * 4) : make_uint2(0, 0);
+      rg[u] = ok ? ldg8(dout + (base + p + u * g.rpi) * lddo + v * 4) : make_uint2(0, 0);
+      dead += ok ? 0 : 1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float f[4], go[4];
+      unpack4(rx[u], f);
+      unpack4(rg[u], go);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float z = fmaf(f[i], A[i], B[i]);
+        const float m = z > 0.f ? 1.f : slope;
+        const float gm = go[i] * m;
+        if (PLAIN) {
+          acc[0][i] += gm;
+          acc[1][i] = fmaf(gm, z, acc[1][i]);
+        } else {
+          acc[0][i] = fmaf(gm, z, acc[0][i]);
+          acc[1][i] += go[i];
+          acc[2][i] += gm;
+          acc[3][i] += m;
+        }
+      }
+    }
+  }
+  if (!PLAIN && dead) {   // a dead row has z = B: take its m out of the count again
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[3][i] -= static_cast<float>(dead) * (B[i] > 0.f ? 1.f : slope);
+  }
+  const int nout = (g.cv < kBlock ? g.cv : kBlock) * 4;   // = c
+#pragma unroll
+  for (int k = 0; k < NKR; ++k) {
+    reduce_cv<4>(acc[k], red, g.cv);
+    for (int idx = threadIdx.x; idx < nout; idx += kBlock)
+      part[(((static_cast<long long>(n) * d + dd) * gridDim.x + blockIdx.x) * c + idx) * NKR + k] =
+          reduce_cv_fetch<4>(red, g.cv, idx);
+    __syncthreads();
+  }
+}
+
+// Second stage: fold the chunks in order, apply the xhat identities, write the R slots (PLAIN: 2 and 4; else all six).
+template <bool PLAIN>
+__global__ void sum_chunks_bwd_kernel(const float* __restrict__ part, int chunks, int c, int d, const float* __restrict__ coef,
+                                      const float* __restrict__ S, float* __restrict__ R, long long total) {
+  constexpr int NKR = PLAIN ? 2 : 4;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;   // (plane, channel)
+  if (i >= total) return;
+  const int ch = static_cast<int>(i % c);
+  const long long plane = i / c;
+  const long long n = plane / d;
+  float t[NKR];
+#pragma unroll
+  for (int k = 0; k < NKR; ++k) t[k] = 0.f;
+  for (int q = 0; q < chunks; ++q) {
+    const float* src = part + ((plane * chunks + q) * c + ch) * NKR;
+#pragma unroll
+    for (int k = 0; k < NKR; ++k) t[k] += src[k];
+  }
+  const float4 cf = __ldg(reinterpret_cast<const float4*>(coef) + n * c + ch);   // {A, B, mean, rstd}
+  const float gamma = cf.x / cf.w;
+  const float beta = fmaf(cf.z, cf.x, cf.y);
+  const float inv_g = gamma != 0.f ? 1.f / gamma : 0.f;   // gamma == 0: xhat is not recoverable from z; those sums read 0
+  float* out = R + i * 6;
+  if (PLAIN) {
+    out[2] = t[0];
+    out[4] = (t[1] - beta * t[0]) * inv_g;
+  } else {
+    out[0] = t[0];
+    out[1] = t[1];
+    out[2] = t[2];
+    out[3] = t[3];
+    out[4] = (t[0] - beta * t[2]) * inv_g;
+    out[5] = (S[i] - beta * t[3]) * inv_g;
+  }
+}
+
 template <bool AFFINE>
 __global__ void __launch_bounds__(kBlock, 4)
 norm_act_bwd_apply4_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo, const __nv_bfloat16* __restrict__ x,
@@ -772,7 +890,8 @@ bool make_grid4(int c, long long hw, spff_shape s, PlaneGrid4* g, dim3* grid) {
   g->hw = static_cast<int>(hw);
   // ~6 waves of blocks over the device (3-4 resident per SM), at least 8 iterations per thread
   const long long planes = static_cast<long long>(s.n) * s.d;
-  long long want_chunks = (24LL * num_sms() + planes - 1) / planes;
+  const long long per_sm = debug_flag(3) > 0 ? debug_flag(3) : 24;   // test hook (spff_debug_set key 3)
+  long long want_chunks = (per_sm * num_sms() + planes - 1) / planes;
   if (want_chunks < 1) want_chunks = 1;
   long long chunk = (hw + want_chunks - 1) / want_chunks;
   const long long min_chunk = 8LL * g->rpi;
@@ -783,7 +902,9 @@ bool make_grid4(int c, long long hw, spff_shape s, PlaneGrid4* g, dim3* grid) {
   return true;
 }
 
-int make_grid(int c, long long hw, spff_shape s, PlaneGrid* g, dim3* grid) {
+// blocks_per_sm: 8 for the kernels that end in a block reduction (their epilogue favours long blocks), 32 for the pure
+// streaming ones (measured: norm_act_apply 5.9 -> 6.5 TB/s, maxpool_bwd_add 4.6 -> 5.0 TB/s at level 1)
+int make_grid(int c, long long hw, spff_shape s, PlaneGrid* g, dim3* grid, int blocks_per_sm = 8) {
   if (c % 8 != 0 || c <= 0 || c > 8 * kBlock) {
     set_error("channel count %d must be a multiple of 8 and <= %d", c, 8 * kBlock);
     return SPFF_ERR_BAD_ARGUMENT;
@@ -793,7 +914,8 @@ int make_grid(int c, long long hw, spff_shape s, PlaneGrid* g, dim3* grid) {
   g->hw = static_cast<int>(hw);
   // aim at >= ~8 blocks per SM overall while keeping >= 16 iterations per block where the plane allows
   const long long planes = static_cast<long long>(s.n) * s.d;
-  long long want_chunks = (8LL * num_sms() + planes - 1) / planes;
+  const long long per_sm = debug_flag(4) > 0 ? debug_flag(4) : blocks_per_sm;    // test hook (spff_debug_set key 4)
+  long long want_chunks = (per_sm * num_sms() + planes - 1) / planes;
   if (want_chunks < 1) want_chunks = 1;
   long long chunk = (hw + want_chunks - 1) / want_chunks;
   const long long min_chunk = 16LL * g->rpi;
@@ -862,7 +984,7 @@ int spff_norm_act_apply(const void* x, long long ldx, const float* coef, void* y
   SPFF_ENTRY_CHECK();
   PlaneGrid g;
   dim3 grid;
-  int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
+  int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid, 32);
   if (e) return e;
   spff::norm_act_kernel<true, false, false><<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(x), ldx, coef, nullptr, nullptr, static_cast<bf16*>(y), ldy, nullptr, g, s.d, c, slope);
@@ -909,7 +1031,7 @@ int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, 
   dim3 grid;
   if (ypool) {
     SPFF_REQUIRE(s.h % 2 == 0 && s.w % 2 == 0, "norm_act_affine_apply: pooling needs even H, W (got %d x %d)", s.h, s.w);
-    int e = spff::make_grid(c, static_cast<long long>(s.h / 2) * (s.w / 2), s, &g, &grid);
+    int e = spff::make_grid(c, static_cast<long long>(s.h / 2) * (s.w / 2), s, &g, &grid, 32);
     if (e) return e;
     if (P)
       spff::norm_act_pool_kernel<true><<<grid, kBlock, 0, st>>>(static_cast<const bf16*>(x), ldx, coef, P, Q,
@@ -920,7 +1042,7 @@ int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, 
                                                                 static_cast<bf16*>(y), ldy, static_cast<bf16*>(ypool),
                                                                 ldp, g, s.d, c, s.h, s.w, slope);
   } else {
-    int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid);
+    int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid, 32);
     if (e) return e;
     if (P)
       spff::norm_act_kernel<true, false, true><<<grid, kBlock, 0, st>>>(
@@ -942,7 +1064,7 @@ size_t spff_norm_act_bwd_reduce_workspace(int c, spff_shape s, int plain) {
 }
 
 int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, long long ldx, const float* coef,
-                             float* R, int c, spff_shape s, float slope, int plain, void* workspace,
+                             float* R, const float* S, int c, spff_shape s, float slope, int plain, void* workspace,
                              size_t workspace_bytes, void* stream) {
   SPFF_ENTRY_CHECK();
   PlaneGrid g;
@@ -955,6 +1077,21 @@ int spff_norm_act_bwd_reduce(const void* dout, long long lddo, const void* x, lo
       const size_t need = spff_norm_act_bwd_reduce_workspace(c, s, plain);
       float* part = (workspace && workspace_bytes >= need) ? static_cast<float*>(workspace) : nullptr;
       SPFF_REQUIRE(!workspace || part, "norm_act_bwd_reduce: workspace too small");
+      if (part && (plain || S)) {   // fixed-order path, lean first stage (the xhat sums follow from the others)
+        const long long total = static_cast<long long>(s.n) * s.d * c;
+        const int blocks = static_cast<int>((total + 255) / 256);
+        if (plain) {
+          spff::norm_act_bwd_reduce4v2_kernel<true><<<grid, kBlock, smem, st4>>>(
+              static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, g4, s.d, c, slope, part);
+          spff::sum_chunks_bwd_kernel<true><<<blocks, 256, 0, st4>>>(part, grid.x, c, s.d, coef, nullptr, R, total);
+        } else {
+          spff::norm_act_bwd_reduce4v2_kernel<false><<<grid, kBlock, smem, st4>>>(
+              static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, g4, s.d, c, slope, part);
+          spff::sum_chunks_bwd_kernel<false><<<blocks, 256, 0, st4>>>(part, grid.x, c, s.d, coef, S, R, total);
+        }
+        SPFF_CUDA(cudaGetLastError());
+        return 0;
+      }
       if (plain)
         spff::norm_act_bwd_reduce4_kernel<true><<<grid, kBlock, smem, st4>>>(
             static_cast<const bf16*>(dout), lddo, static_cast<const bf16*>(x), ldx, coef, R, g4, s.d, c, slope, part);
@@ -1027,7 +1164,7 @@ int spff_maxpool_bwd_add(const void* dpool, long long ldp, const void* y, long l
   SPFF_REQUIRE(s.h % 2 == 0 && s.w % 2 == 0, "maxpool_bwd_add: needs even H, W");
   PlaneGrid g;
   dim3 grid;
-  int e = spff::make_grid(c, static_cast<long long>(s.h / 2) * (s.w / 2), s, &g, &grid);
+  int e = spff::make_grid(c, static_cast<long long>(s.h / 2) * (s.w / 2), s, &g, &grid, 32);
   if (e) return e;
   spff::maxpool_bwd_add_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(dpool), ldp, static_cast<const bf16*>(y), ldy, static_cast<bf16*>(dskip), ldd, g, s.d,

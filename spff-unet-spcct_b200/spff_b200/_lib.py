@@ -64,7 +64,7 @@ _PROTOTYPES = {
     "spff_norm_act_affine_apply": [_P, _LL, _P, _P, _P, _P, _LL, _P, _LL, c_int, Shape, c_float, _P],
     "spff_gate_micro_fwd": [_P] * 8 + [c_int, c_int, c_int, Shape, _P, _P, _P],
     "spff_norm_act_bwd_reduce_workspace": [c_int, Shape, c_int],
-    "spff_norm_act_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, c_int, Shape, c_float, c_int, _P, c_size_t, _P],
+    "spff_norm_act_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, _P, c_int, Shape, c_float, c_int, _P, c_size_t, _P],
     "spff_gate_micro_bwd": [_P] * 11 + [c_int, c_int, c_int, Shape] + [_P] * 12 + [_P],
     "spff_norm_act_bwd_apply": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _LL, c_int, Shape, c_float, _P],
     "spff_maxpool_bwd_add": [_P, _LL, _P, _LL, _P, _LL, c_int, Shape, c_int, _P],

@@ -383,8 +383,8 @@ class SpffEngine:
         t1, t2 = B.t1[l], B.t2[l]
         # tail + IN2 + lrelu backward
         R2 = B.b32.get(B.idx[f"{b}.R2"])
-        ops.norm_act_bwd_reduce(dout, B.x2[b], B.coef[f"{b}.2"], R2, c, SLOPE, plain=(flags == 0), fixed_order=True)
         S = B.f32.get(B.idx[f"{b}.S"]) if flags else None
+        ops.norm_act_bwd_reduce(dout, B.x2[b], B.coef[f"{b}.2"], R2, c, SLOPE, plain=(flags == 0), fixed_order=True, S=S)
         dse = None
         if flags & GATE_CHANSE:
             i = _STAGE[b]

@@ -213,15 +213,16 @@ def gate_micro_fwd(S, g1, bt, kfg, se, flags, c, shape, P, Q):
          shape, ptr(P), ptr(Q), stream_ptr())
 
 
-def norm_act_bwd_reduce(dout, x, coef, R, c, slope, plain=False, fixed_order=False):
-    """plain=True: only the two sums the gate-free InstanceNorm + LeakyReLU backward needs."""
+def norm_act_bwd_reduce(dout, x, coef, R, c, slope, plain=False, fixed_order=False, S=None):
+    """plain=True: only the two sums the gate-free InstanceNorm + LeakyReLU backward needs.
+    S: the forward statistic of the same tensor (norm_act_reduce); with fixed_order it enables the lean first stage."""
     s, lddo = _view(dout, c)
     _, ldx = _view(x, c)
     ws, nbytes = None, 0
     if fixed_order:
         nbytes = int(_lib.lib.spff_norm_act_bwd_reduce_workspace(c, s, int(plain)))
         ws = workspace(nbytes, x.device) if nbytes else None
-    call("spff_norm_act_bwd_reduce", ptr(dout), lddo, ptr(x), ldx, ptr(coef), ptr(R), c, s, float(slope), int(plain),
+    call("spff_norm_act_bwd_reduce", ptr(dout), lddo, ptr(x), ldx, ptr(coef), ptr(R), ptr(S), c, s, float(slope), int(plain),
          ptr(ws), ws.numel() if ws is not None else 0, stream_ptr())
 
 

@@ -152,6 +152,41 @@ def test_spff_tail_fwd_bwd(flags, n, c, d, h, w):
         assert rel(dse[3].cpu(), p["sb2"].grad.cpu()) < 5e-3
 
 
+@pytest.mark.parametrize("n,c,d,h,w", [(2, 32, 5, 16, 16), (3, 64, 5, 24, 8), (2, 256, 5, 4, 4), (1, 128, 16, 8, 8), (1, 512, 1, 4, 4)])
+def test_bwd_reduce_lean_path_matches_direct_sums(n, c, d, h, w):
+    """Fixed-order path with the lean first stage (xhat sums derived from {dout*a, dout*m, m, S}) == the direct sums
+    of the original kernel, for the full (gated) and the plain statistics, ragged chunk tails included."""
+    from spff_b200 import ops
+    torch.manual_seed(7)
+    x = torch.randn(n, c, d, h, w, device="cuda") * 1.3 + 0.4
+    gamma = torch.rand(c, device="cuda") + 0.5
+    gamma[1] = -0.7
+    beta = torch.randn(c, device="cuda") * 0.3
+    xb = pm(x)
+    dob = pm(torch.randn(n, c, d, h, w, device="cuda"))
+    coef = _coef(xb, c, gamma, beta)
+    S = torch.zeros(n, d, c, device="cuda")
+    ops.norm_act_reduce(xb, coef, S, c, 0.01)
+    direct = torch.zeros(n, d, c, 6, device="cuda")
+    ops.norm_act_bwd_reduce(dob, xb, coef, direct, c, 0.01)
+    scale = direct.abs().amax(dim=(0, 1, 2), keepdim=True) + 1e-6
+    lean = torch.full((n, d, c, 6), float("nan"), device="cuda")
+    ops.norm_act_bwd_reduce(dob, xb, coef, lean, c, 0.01, fixed_order=True, S=S)
+    assert float(((lean - direct) / scale).abs().max()) < 2e-4
+    lean2 = torch.full((n, d, c, 6), float("nan"), device="cuda")
+    ops.norm_act_bwd_reduce(dob, xb, coef, lean2, c, 0.01, fixed_order=True, S=S)
+    assert torch.equal(lean, lean2)                      # fixed order: bit-reproducible
+    plain = torch.zeros(n, d, c, 6, device="cuda")
+    ops.norm_act_bwd_reduce(dob, xb, coef, plain, c, 0.01, plain=True, fixed_order=True)
+    assert float(((plain[..., [2, 4]] - direct[..., [2, 4]]) / scale[..., [2, 4]]).abs().max()) < 2e-4
+    # ReLU (slope 0), as the 3DUNet control runs it
+    direct0 = torch.zeros(n, d, c, 6, device="cuda")
+    ops.norm_act_bwd_reduce(dob, xb, coef, direct0, c, 0.0, plain=True)
+    plain0 = torch.zeros(n, d, c, 6, device="cuda")
+    ops.norm_act_bwd_reduce(dob, xb, coef, plain0, c, 0.0, plain=True, fixed_order=True)
+    assert float(((plain0[..., [2, 4]] - direct0[..., [2, 4]]) / scale[..., [2, 4]]).abs().max()) < 2e-4
+
+
 def test_tail_table_grads():
     """Gradients reaching the EFiLM MLP and the FourierGate mask through the CUDA tables path."""
     from spff_b200 import ops, tables
