@@ -326,6 +326,95 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_infer(args):
+    """--mode infer: BASELINE.json configs[4] — SPFF-UNet inference over a synthetic 5x512x512x256 scan = x[256,1,5,512,512],
+    whole z-slices sharded over the ranks with no collective; output: the uint8 label map (argmax fused
+    into the head kernel). A "step" is one pass over the rank's shard. Not the headline metric: an extra line."""
+    import torch
+    import torch.distributed as dist
+
+    from innovative3D import config as C
+    from spff_b200 import _lib, dp
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    slices, hh, ww = int(os.environ.get("SPFF_INFER_SLICES", 256)), 512, 512
+    lo, hi = dp.shard_range(slices, rank, world)
+    torch.manual_seed(42)
+    lit = dict((v[0], v[1]) for v in C.VARIANTS)["SPFF-UNet"]().to(dev).eval()
+    g = torch.Generator().manual_seed(99 + rank)
+    x_host = torch.randn(hi - lo, 1, FRAMES, hh, ww, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.empty(hi - lo, FRAMES, hh, ww, dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t) * 1e-3
+
+    def step_resident():
+        return lit.model.predict_labels(x_dev)
+
+    def step_e2e():
+        out_host.copy_(lit.model.predict_labels(x_host.to(dev, non_blocking=True)), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local)
+    clocks.start()
+    calls0 = _lib.CALLS
+    sec = timed(step_resident, args.steps)
+    launches = _lib.CALLS - calls0
+    clk = clocks.stop()
+    step_e2e()
+    sec_e2e = timed(step_e2e, args.steps)
+    if rank == 0:
+        vox = slices * FRAMES * hh * ww
+        peaks, peak_kind = load_peaks()
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        fwd_flop = 816_640     # SURVEY.md §8d: forward FLOP per voxel
+        print(json.dumps({
+            "metric": "SPFF-UNet inference voxels/s", "value": vox * args.steps / sec, "unit": "voxels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"SPFF-UNet inference, synthetic scan 5x512x512x{slices} = x[{slices},1,5,512,512] "
+                                   f"(BASELINE.json configs[4]), whole z-slices sharded over {world} rank(s), no collective",
+                       "slices_per_gpu": hi - lo, "output": "uint8 label map (argmax fused into the head kernel)",
+                       "l2": "inputs larger than L2"},
+            "clocks": clk,
+            "e2e": {"value": vox * args.steps / sec_e2e, "unit": "voxels/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel(), "ms_per_step": sec_e2e / args.steps * 1e3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "whole forward (816 640 FLOP/voxel dense)",
+                         "achieved": vox / world * args.steps / sec * fwd_flop / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": vox / world * args.steps / sec * fwd_flop / 1e12 / peak, "traffic": None,
+                         "peak_kind": f"{peak_kind} sustained bf16"},
+        }), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -336,9 +425,13 @@ def main():
     ap.add_argument("--variant", default="SPFF-UNet",
                     choices=["SPFF-UNet", "E_SP_UNet", "FG_SP_UNet", "SP_UNet", "PlainCore_UNet", "3DUNet"],
                     help="SPFF-UNet is the headline (BASELINE.json configs[1]); the others are the controls of configs[3]")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train: the headline step (default); infer: BASELINE.json configs[4], an extra line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "infer":
+        run_infer(args)
     else:
         run_b200(args)
 

@@ -273,6 +273,7 @@ class SpffEngine:
         self._packed: Dict[str, Tuple[torch.Tensor, Optional[torch.Tensor]]] = {}
         self._packed_key = None
         self._bufs: Dict[tuple, _GroupBuffers] = {}
+        self._fit: Dict[tuple, int] = {}
 
     # ------------------------------------------------------------------------------------------
     def params(self) -> Dict[str, torch.Tensor]:
@@ -463,6 +464,28 @@ class SpffEngine:
         return x.float().contiguous()
 
     @staticmethod
+    def fit_group(group: int, d: int, h: int, w: int, device, train: bool) -> int:
+        """Largest sample group <= `group` whose buffers fit in ~45 % of the free HBM. One sample holds, in units of
+        one level-1 32-channel bf16 tensor (d*h*w*64 bytes): x1/a1/x2/out per block, the concat and pooled buffers
+        (16.7 units forward) plus the gradient scratch (26.5 units for a training step)."""
+        per = (26.5 if train else 16.7) * d * h * w * 64
+        try:
+            free, _ = torch.cuda.mem_get_info(device)
+        except Exception:
+            return max(1, group)
+        return max(1, min(group, int(0.45 * free / per)))
+
+    def _fitted(self, group: int, d: int, h: int, w: int, device, train: bool) -> int:
+        """fit_group, decided once per (shape, mode, requested group) — before that shape's buffers exist, when the
+        free-memory reading still describes what is available to them."""
+        key = (group, d, h, w, str(device), train)
+        if key not in self._fit:
+            if not any(k[1:4] == (d, h, w) for k in self._bufs):
+                self._bufs.clear()          # buffers of another slice size would otherwise count as unavailable
+            self._fit[key] = self.fit_group(group, d, h, w, device, train)
+        return self._fit[key]
+
+    @staticmethod
     def _groups(batch: int, group: int):
         group = max(1, min(group, batch))
         return [(i, min(batch, i + group)) for i in range(0, batch, group)]
@@ -478,6 +501,7 @@ class SpffEngine:
             out = torch.empty(bsz, d, h, w, dtype=torch.uint8, device=x.device)
         else:
             out = torch.empty(bsz, self.cfg.num_classes, d, h, w, device=x.device)
+        group = self._fitted(min(group, bsz), d, h, w, x.device, train=False)
         for lo, hi in self._groups(bsz, group):
             B = self.buffers(hi - lo, d, h, w, x.device, train=False)
             if argmax:
@@ -525,6 +549,7 @@ class SpffEngine:
             raise ValueError(f"labels must be [B,F,H,W] = {(bsz, d, h, w)}, got {tuple(labels.shape)}")
         labels = labels.contiguous()
         self.refresh_weights()
+        group = self._fitted(min(group, bsz), d, h, w, x.device, train=True)
         T = GateTables(self.cfg, self.params(), d, need_grad=True)
         n_valid = None
         p = self.params()
