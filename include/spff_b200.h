@@ -258,6 +258,25 @@ int spff_sgd_step(float* param, const float* grad, float* momentum_buf, long lon
 int spff_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* ---- data path feeding the step -------------------------------------------------------
+ * Phantom label rasterisation: labels[f][y][x] (int64, frames x height x width) = label of the LAST roi
+ * (x0, y0, w0, h0, label — HOST array of nroi x 5 ints, nroi <= 64) whose inscribed ellipse contains the pixel,
+ * else 0: the per-pixel loop of create_image_and_labels_for_dataset + is_pixel_in_ellipse
+ * (helpers.py:125-129, 197-206), double arithmetic in the reference's order, numpy's negative-index wrap. */
+int spff_roi_labels(const int* rois_host, int nroi, int frames, int height, int width, long long* labels, void* stream);
+/* TrainGridAug (datasets.py:134-206) over a batch: xo[n][f][h][w] = jitter(x[n][f][A[u]][B[v]]) (+ noise, + stamp),
+ * (u, v) = (h, w) or, for transposed[n] != 0 (odd rot90; needs h == w), (w, h); labels gathered the same way.
+ * amap [n][h], bmap [n][w]: the composition of the flips, the rotation and the stripe shuffle
+ * (_shuffle_stripes, datasets.py:56-121) drawn by the host; scale/shift [n]: x*scale + shift (1, 0 = none);
+ * noise_cap [n]: noise_std of samples that get noise (amplitude min(noise_cap, 0.25*std(x)), datasets.py:180-184),
+ * 0 = none; seed [n]; stamp [n]: non-zero writes x[n][0][:32][:32] = max(region) + max(max|x|, 1)*0.25
+ * (datasets.py:196-201). x fp32 [n][frames][h][w]; y uint8 / int64 or NULL. Not in place. */
+size_t spff_grid_aug_workspace(int n);
+int spff_grid_aug(const float* x, const void* y, int label_bytes, float* xo, void* yo, int n, int frames, int h, int w,
+                  const int* amap, const int* bmap, const int* transposed, const float* scale, const float* shift,
+                  const float* noise_cap, const unsigned long long* seed, const int* stamp, int any_noise, int any_stamp,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,12 +90,16 @@ _PROTOTYPES = {
     "spff_maxpool222_fwd": [_P, _LL, _P, _LL, c_int, Shape, _P],
     "spff_maxpool222_bwd_add": [_P, _LL, _P, _LL, _P, _LL, c_int, Shape, c_int, _P],
     "spff_sgd_step": [_P, _P, _P, _LL, c_float, c_float, c_float, c_int, c_int, c_float, _P],
+    "spff_roi_labels": [_P, c_int, c_int, c_int, c_int, _P, _P],
+    "spff_grid_aug_workspace": [c_int],
+    "spff_grid_aug": [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P,
+                      c_size_t, _P],
 }
 
 _SIZE_T_FUNCS = {"spff_conv3d_k3_wgrad_workspace", "spff_conv3d_stem_wgrad_workspace",
                  "spff_convt_k122_wgrad_workspace", "spff_head_bwd_workspace", "spff_head_loss_workspace",
                  "spff_norm_act_reduce_workspace", "spff_norm_act_bwd_reduce_workspace",
-                 "spff_convt_k222_wgrad_workspace", "spff_bn_coeffs_workspace"}
+                 "spff_convt_k222_wgrad_workspace", "spff_bn_coeffs_workspace", "spff_grid_aug_workspace"}
 
 
 def _declare():

@@ -392,3 +392,31 @@ def maxpool222_bwd_add(dpool, y, dskip, c, accumulate):
 def sgd_step(p, g, buf, lr, momentum, weight_decay, nesterov, first_step, grad_scale=1.0):
     call("spff_sgd_step", ptr(p), ptr(g), ptr(buf), p.numel(), float(lr), float(momentum), float(weight_decay),
          int(bool(nesterov)), int(bool(first_step)), float(grad_scale), stream_ptr())
+
+
+# ------------------------------------------------------------------------------------------------
+# data path
+# ------------------------------------------------------------------------------------------------
+def roi_labels(rois, frames, height, width, device) -> torch.Tensor:
+    """int64 [frames, height, width] label map of elliptical rois [(x0, y0, w0, h0, label), ...] (last one wins)."""
+    import ctypes
+    flat = [int(v) for r in rois for v in r]
+    arr = (ctypes.c_int * max(1, len(flat)))(*flat)
+    out = torch.empty(frames, height, width, dtype=torch.int64, device=device)
+    with torch.cuda.device(out.device):
+        call("spff_roi_labels", arr, len(rois), frames, height, width, ptr(out), stream_ptr())
+    return out
+
+
+def grid_aug(x, y, xo, yo, amap, bmap, transposed, scale, shift, noise_cap, seed, stamp, any_noise, any_stamp):
+    """x fp32 [n,F,H,W] -> xo; y uint8/int64 [n,F,H,W] or None -> yo; the per-sample tables are CUDA tensors."""
+    n, f, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and xo.is_contiguous() and xo.shape == x.shape
+    lb = 0
+    if y is not None:
+        assert y.is_contiguous() and yo.is_contiguous() and tuple(y.shape) == (n, f, h, w) and y.dtype == yo.dtype
+        lb = _label_bytes(y)
+    assert amap.dtype == torch.int32 and bmap.dtype == torch.int32 and tuple(amap.shape) == (n, h) and tuple(bmap.shape) == (n, w)
+    ws = workspace(int(_lib.lib.spff_grid_aug_workspace(n)), x.device)
+    call("spff_grid_aug", ptr(x), ptr(y), lb, ptr(xo), ptr(yo), n, f, h, w, ptr(amap), ptr(bmap), ptr(transposed), ptr(scale),
+         ptr(shift), ptr(noise_cap), ptr(seed), ptr(stamp), int(any_noise), int(any_stamp), ptr(ws), ws.numel(), stream_ptr())
