@@ -126,9 +126,10 @@ struct AugParams {
 template <typename LabelT>
 __global__ void __launch_bounds__(256) grid_aug_kernel(const float* __restrict__ x, const LabelT* __restrict__ y,
                                                        float* __restrict__ xo, LabelT* __restrict__ yo, AugParams p) {
-  const int n = blockIdx.z, hh = blockIdx.y;
-  const int ww = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool ok = ww < p.w;
+  const int n = blockIdx.y;
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;     // flattened (h, w): full blocks whatever the row length
+  const bool ok = pos < p.h * p.w;
+  const int hh = ok ? pos / p.w : 0, ww = ok ? pos % p.w : 0;
   const int tr = p.transposed[n];
   int sh = 0, sw = 0;
   if (ok) {
@@ -231,7 +232,8 @@ int spff_grid_aug(const float* x, const void* y, int label_bytes, float* xo, voi
   SPFF_REQUIRE(x != xo && (!y || y != yo), "grid_aug: the gather cannot run in place");
   SPFF_REQUIRE((y == nullptr) == (yo == nullptr) && (!y || label_bytes == 1 || label_bytes == 8),
                "grid_aug: labels must be uint8 or int64, given with their output");
-  SPFF_REQUIRE(n > 0 && n <= 65535 && frames > 0 && h > 0 && h <= 65535 && w > 0, "grid_aug: bad shape");
+  SPFF_REQUIRE(n > 0 && n <= 65535 && frames > 0 && h > 0 && w > 0 && static_cast<long long>(h) * w < (1LL << 30),
+               "grid_aug: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* stats = nullptr;
   int* maxima = nullptr;
@@ -255,7 +257,7 @@ int spff_grid_aug(const float* x, const void* y, int label_bytes, float* xo, voi
   if (any_stamp) spff::init_maxima_kernel<<<(n + 127) / 128, 128, 0, st>>>(maxima, n);
   spff::AugParams p{n, frames, h, w, amap, bmap, transposed, scale, shift, noise_cap, seed, any_noise ? stats : nullptr,
                     any_stamp ? maxima : nullptr};
-  dim3 grid((w + 255) / 256, h, n);
+  dim3 grid((h * w + 255) / 256, n);
   if (!y)
     spff::grid_aug_kernel<unsigned char><<<grid, 256, 0, st>>>(x, nullptr, xo, nullptr, p);
   else if (label_bytes == 1)
