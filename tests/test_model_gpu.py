@@ -171,6 +171,31 @@ def test_trained_weights_meet_north_star_tolerances(variant):
     assert not tiny or max(tiny.values()) < 0.15, sorted(tiny.items(), key=lambda kv: -kv[1])[:5]
 
 
+def test_config1_batch_against_oracle():
+    """BASELINE.json configs[0] — the reference's own CPU-runnable case: SPFF-UNet fwd+bwd on the synthetic 5-bin batch
+    2 x 5 x 64^3 = x[128,1,5,64,64], 13 classes, seed 42 (reference-identical initialisation, then 60 fused steps so that
+    the comparison is not on random-init logits): loss, whole-gradient and argmax agreement against the CPU fp32 oracle on
+    the full batch, through fit_step in sample groups of 48 (ragged last group)."""
+    from oracle import spff_oracle as O
+    torch.manual_seed(42)
+    lit = build("SPFF-UNet")
+    _train(lit, 60, 8, 32, 32, 1e-3)
+    sd = {k: v.detach().cpu().clone() for k, v in lit.state_dict().items() if not k.endswith("fgate._mask")}
+    x, lab = O.phantom_batch(128, 64, 64, seed=42, ignore_frac=0.01)
+    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd, x, lab, "SPFF-UNet")
+    out = lit.fit_step((x.cuda(), lab.cuda()), optimize=False, sample_group=48)
+    assert abs(float(out["loss"]) - ref_loss) < 1e-2 * max(1.0, abs(ref_loss))
+    G = lit.fused_grads()
+    num = sum(float((g.cpu().double() - ref_grads["model." + n].double()).pow(2).sum()) for n, g in G.items())
+    den = sum(float(ref_grads["model." + n].double().pow(2).sum()) for n in G)
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5
+    labels = lit.model.predict_labels(x.cuda())
+    assert float((labels.cpu().long() == ref_logits.argmax(1)).float().mean()) >= 0.999
+    m = lit.step_metrics(out["tally"], lab.numel())
+    mo = O.per_class_metrics_3d(ref_logits, lab, 13, ignore_index=255)
+    assert abs(m[3] - mo[3]) < 1e-3
+
+
 def test_taps_per_block_activations():
     """Per-block outputs (encoder skips, bottleneck, decoders) vs the oracle's taps on fixture weights."""
     from oracle import spff_oracle as O
