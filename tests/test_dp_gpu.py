@@ -62,3 +62,56 @@ def test_two_rank_step_equals_single_process_step():
     # summation orders, so parameters agree to within 2 lr element-wise (and closely in the mean)
     diff = (out[0]["flat"] - lit.model._flat.detach().cpu()).abs()
     assert float(diff.max()) <= 2.1e-3 and float((diff > 1e-4).float().mean()) < 0.05
+
+
+def _worker_3dunet(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from innovative3D import config as C
+    from oracle import cicek_oracle as CO
+    from oracle import spff_oracle as O
+    lit = dict((v[0], v[1]) for v in C.VARIANTS)["3DUNet"]().cuda()
+    lit.load_state_dict(CO.det_weights(seed=42), strict=True)
+    lit.train()
+    x, lab = O.phantom_batch(4, 32, 32, seed=78)
+    lo, hi = rank * 2, rank * 2 + 2
+    o = lit.fit_step((x[lo:hi].cuda(), lab[lo:hi].cuda()))
+    torch.cuda.synchronize()
+    out[rank] = dict(grad=lit._fused["grad"].cpu(), flat=lit.backbone._flat.detach().cpu(), loss=float(o["loss"]),
+                     rm=lit.state_dict()["backbone.enc1.1.running_mean"].cpu())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_3dunet_step():
+    """3DUNet under data parallelism: per-rank BatchNorm statistics (no SyncBN), ONE all-reduce, the same
+    SGD step on every rank — the reduced gradient is the sum of the two shards' single-process gradients, and the
+    parameters equal a single-process SGD step with their mean."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_3dunet, args=(world, _free_port(), out), nprocs=world, join=True)
+    from innovative3D import config as C
+    from oracle import cicek_oracle as CO
+    from oracle import spff_oracle as O
+    from spff_b200 import ops
+    x, lab = O.phantom_batch(4, 32, 32, seed=78)
+    weights = CO.det_weights(seed=42)
+    shard = []
+    for r in range(world):
+        lit = dict((v[0], v[1]) for v in C.VARIANTS)["3DUNet"]().cuda()
+        lit.load_state_dict(weights, strict=True)
+        lit.train()
+        lit.fit_step((x[2 * r:2 * r + 2].cuda(), lab[2 * r:2 * r + 2].cuda()), optimize=False)
+        shard.append(lit._fused["grad"].clone())
+        assert torch.equal(lit.state_dict()["backbone.enc1.1.running_mean"].cpu(), out[r]["rm"])   # per-rank statistics
+    assert torch.equal(out[0]["grad"], out[1]["grad"]) and torch.equal(out[0]["flat"], out[1]["flat"])
+    assert torch.equal(out[0]["grad"], (shard[0] + shard[1]).cpu())
+    flat = lit.backbone._flat.detach().clone()     # still the initial weights (optimize=False)
+    buf = torch.zeros_like(flat)
+    ops.sgd_step(flat, shard[0] + shard[1], buf, 1e-2, 0.99, 0.0, False, True, 0.5)
+    assert torch.equal(flat.cpu(), out[0]["flat"])
+    assert not torch.equal(out[0]["rm"], out[1]["rm"])
