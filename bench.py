@@ -374,9 +374,8 @@ def run_infer(args):
     def step_resident():
         return lit.model.predict_labels(x_dev)
 
-    def step_e2e():
-        out_host.copy_(lit.model.predict_labels(x_host.to(dev, non_blocking=True)), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def step_e2e():      # images streamed in and label maps streamed out group by group; complete on return
+        lit.model.predict_labels_streamed(x_host, out_host)
 
     for _ in range(max(args.warmup, 3)):
         step_resident()

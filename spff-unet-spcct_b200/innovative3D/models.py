@@ -352,6 +352,25 @@ class UNet3D_SpectralCore(nn.Module):
         return self.engine.infer(x.to(self.out.weight.device), group=self.sample_group, argmax=True)
 
 
+    @torch.no_grad()
+    def predict_labels_streamed(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`predict_labels` for a scan held in host memory (pinned for overlap): images stream in and label maps
+        stream out group by group on a copy stream while the kernels run. Returns the host uint8 [B,F,H,W] tensor
+        (complete on return)."""
+        x_host = _pick_first_if_seq(x_host)
+        if x_host.ndim == 4:
+            x_host = x_host.unsqueeze(1)
+        self.materialize(x_host.shape[2])
+        dev = self.out.weight.device
+        if out_host is None:
+            out_host = torch.empty(x_host.shape[0], *x_host.shape[2:], dtype=torch.uint8).pin_memory()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        self.engine.infer_streamed(x_host, out_host, dev, self._copy_stream, group=self.sample_group)
+        self._copy_stream.synchronize()
+        return out_host
+
+
 def upgrade_spct_with_novel_blocks(m: nn.Module, use_efilm: bool = True, use_fouriergate: bool = True,
                                    use_moe: bool = False, moe_K: int = 3):
     """Replace every `_DoubleConvSpectral` child by the novel block, keeping channels

@@ -510,6 +510,52 @@ class SpffEngine:
                 self.forward_group(B, T, x[lo:hi], head="logits", logits_out=out[lo:hi])
         return out
 
+    def infer_streamed(self, x_host: torch.Tensor, out_host: torch.Tensor, device, copy_stream: torch.cuda.Stream,
+                       group: int = 32) -> None:
+        """Label maps of a scan that lives in (pinned) HOST memory, written to a (pinned) host uint8 tensor [B,F,H,W]:
+        group g+1 is copied in and the labels of group g-1 are copied out on `copy_stream` while group g computes, so
+        neither transfer is exposed. The last device->host copy is complete when `copy_stream` is synchronised."""
+        if x_host.dim() != 5 or x_host.shape[1] != 1 or x_host.is_cuda or out_host.is_cuda:
+            raise ValueError("infer_streamed takes host tensors: images [B,1,F,H,W] and a uint8 output [B,F,H,W]")
+        bsz, _, d, h, w = x_host.shape
+        if tuple(out_host.shape) != (bsz, d, h, w) or out_host.dtype != torch.uint8:
+            raise ValueError(f"out_host must be uint8 {(bsz, d, h, w)}")
+        self.refresh_weights()
+        T = GateTables(self.cfg, self.params(), d, need_grad=False)
+        group = self._fitted(min(group, bsz), d, h, w, device, train=False)
+        groups = self._groups(bsz, group)
+        main = torch.cuda.current_stream(device)
+        src = x_host if x_host.dtype == torch.float32 else x_host.float()
+        xin = [torch.empty(group, 1, d, h, w, device=device) for _ in range(2)]         # double-buffered input
+        lab = [torch.empty(group, d, h, w, dtype=torch.uint8, device=device) for _ in range(2)]
+        loaded, computed, stored = {}, {}, {}
+        copy_stream.wait_stream(main)
+
+        def load(i):
+            lo, hi = groups[i]
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(computed[i - 2])      # the buffer's previous group has been consumed
+                xin[i % 2][:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                loaded[i] = copy_stream.record_event()
+
+        load(0)
+        for i, (lo, hi) in enumerate(groups):
+            if i + 1 < len(groups):
+                load(i + 1)
+            main.wait_event(loaded[i])
+            if i >= 2:
+                main.wait_event(stored[i - 2])                    # its label buffer has been copied out
+            B = self.buffers(hi - lo, d, h, w, device, train=False)
+            self.forward_group(B, T, xin[i % 2][:hi - lo], head="argmax", labels_out=lab[i % 2][:hi - lo])
+            computed[i] = main.record_event()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(computed[i])
+                out_host[lo:hi].copy_(lab[i % 2][:hi - lo], non_blocking=True)
+                stored[i] = copy_stream.record_event()
+        for t in xin + lab:
+            t.record_stream(copy_stream)
+
     def forward_saved(self, x: torch.Tensor, group: int = 32):
         """Forward that keeps every group's activations for a later `backward_saved` (the autograd
         path behind `model(x)`; memory grows with the batch, unlike `train_step`)."""

@@ -236,6 +236,19 @@ def test_inference_native_slice_size_and_sharding():
     assert acc > 0.5, acc      # 80 steps on phantoms already segment most of the slice
 
 
+def test_streamed_inference_equals_resident():
+    """predict_labels_streamed (host in, host out, double-buffered groups on a copy stream) == predict_labels."""
+    torch.manual_seed(3)
+    lit = build("SPFF-UNet").eval()
+    x = torch.randn(7, 1, 5, 64, 48)
+    lit.model.sample_group = 2                       # 4 groups, ragged last one
+    want = lit.model.predict_labels(x.cuda()).cpu()
+    got = lit.model.predict_labels_streamed(x.pin_memory())
+    assert got.dtype == torch.uint8 and not got.is_cuda and torch.equal(got, want)
+    got2 = lit.model.predict_labels_streamed(x)      # pageable source works too
+    assert torch.equal(got2, want)
+
+
 def test_native_batch_of_one_slice_training_step():
     """The reference trains with BATCH_SIZE = 1 on whole 512x512 slices (config.py:21,27): the fused step and the
     Lightning-style path (model -> loss -> backward) agree at that shape, and rectangular slices work."""
