@@ -93,6 +93,11 @@ int spff_conv3d_k3_wgrad(const void* x, long long ldx, int cin, const void* dy, 
  * x is the network input as the reference holds it: fp32 [N,1,D,H,W] contiguous. w fp32 [cout][1][3][3][3]. */
 int spff_conv3d_stem_fwd(const float* x, const float* w, void* y, long long ldy, int cout, spff_shape s,
                          void* stream);
+/* Forward + statistics of the output in the epilogue: stat_partial[n][slots][2][cout] with
+ * slots = spff_conv3d_stem_stat_slots(s), reduced by spff_in_coeffs_from_partials / spff_bn_coeffs (cout must be 32). */
+int spff_conv3d_stem_stat_slots(spff_shape s);
+int spff_conv3d_stem_fwd_stats(const float* x, const float* w, void* y, long long ldy, int cout, spff_shape s,
+                               float* stat_partial, void* stream);
 size_t spff_conv3d_stem_wgrad_workspace(int cout);
 /* dw[cout][1][3][3][3] = beta*dw + gradient (per-block partials in `workspace`, fixed-order reduce). */
 int spff_conv3d_stem_wgrad(const float* x, const void* dy, long long lddy, int cout, spff_shape s, float* dw,

@@ -124,6 +124,90 @@ stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_b
   }
 }
 
+// The same convolution with the InstanceNorm / BatchNorm statistics of its output taken in the epilogue (fp32
+// accumulators, before the bf16 rounding): grid = (slots, n), a block strides over the items of ONE sample and
+// writes one partial row partial[n][slot][2][cout] = {sum, sum of squares} — the layout of the tensor-core conv's
+// epilogue partials, reduced in a fixed order by spff_in_coeffs_from_partials / spff_bn_coeffs. Replaces the
+// separate spff_in_stats pass over the stem output.
+__global__ void __launch_bounds__(256)
+stem_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
+                      int cout, spff_shape s, float* __restrict__ partial) {
+  extern __shared__ float sw[];  // [27][cout], then [8 warps][2][cout] for the block reduction
+  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) sw[(i % 27) * cout + i / 27] = w[i];
+  __syncthreads();
+  float* red = sw + 27 * cout;
+  const int c8 = cout / 8;                       // a power of two <= 32 (checked by the host)
+  const int strips = (s.w + kStrip - 1) / kStrip;
+  const long long per_sample = static_cast<long long>(s.d) * s.h * strips * c8;
+  const long long n0 = static_cast<long long>(blockIdx.y) * per_sample;
+  float ssum[8], ssq[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ssum[k] = ssq[k] = 0.f;
+  // the stride is a multiple of c8: a thread keeps its channel vector v for all its items
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_sample;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int v, w0, hq, dq;
+    long long rowbase;
+    stem_decode(n0 + i, c8, strips, s, v, w0, hq, dq, rowbase);
+    float acc[kStrip][8];
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        float xw[kStrip + 2];
+        stem_window(x, rowbase, w0, hq, dq, kd, kh, s, xw);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float4* wr = reinterpret_cast<const float4*>(sw + ((kd * 3 + kh) * 3 + kw) * cout + v * 8);
+          const float4 wa = wr[0], wb = wr[1];
+          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int j = 0; j < kStrip; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(xw[j + kw], wv[k], acc[j][k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kStrip; ++j) {
+      if (w0 + j < s.w) {
+        *reinterpret_cast<uint4*>(y + (rowbase + w0 + j) * ldy + v * 8) = pack8(acc[j]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          ssum[k] += acc[j][k];
+          ssq[k] = fmaf(acc[j][k], acc[j][k], ssq[k]);
+        }
+      }
+    }
+  }
+  // lanes with the same v (lane % c8) fold by shuffles, the 8 warps meet in shared memory, fixed order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int off = 16; off >= c8; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], off);
+      ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], off);
+    }
+  }
+  if (lane < c8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[(warp * 2 + 0) * cout + lane * 8 + k] = ssum[k];
+      red[(warp * 2 + 1) * cout + lane * 8 + k] = ssq[k];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * cout; idx += blockDim.x) {
+    float t = 0.f;
+    for (int wp = 0; wp < 8; ++wp) t += red[wp * 2 * cout + idx];
+    partial[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 2 * cout + idx] = t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Stem weight gradient on the tensor cores. dw[tap][co] = sum_pos x[pos + off(tap)] * dy[pos][co] is a
 // GEMM with M = 27 taps (padded to 32), N = 32 output channels, K = positions. The operands are far
@@ -1034,6 +1118,31 @@ int spff_conv3d_stem_fwd(const float* x, const float* w, void* y, long long ldy,
   const int grid = spff::grid_for(total, 256, 16);
   spff::stem_fwd_kernel<<<grid, 256, 27 * cout * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       x, w, static_cast<bf16*>(y), ldy, cout, s);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_conv3d_stem_stat_slots(spff_shape s) {
+  if (s.n <= 0 || s.d <= 0 || s.h <= 0 || s.w <= 0) return 0;
+  // ~16 blocks per SM over the whole launch, at least 4 items per thread
+  const long long per_sample = static_cast<long long>(s.d) * s.h * ((s.w + spff::kStrip - 1) / spff::kStrip) * 4;
+  long long slots = (16LL * spff::num_sms() + s.n - 1) / s.n;
+  const long long cap = (per_sample + 4 * 256 - 1) / (4 * 256);
+  if (slots > cap) slots = cap;
+  if (slots < 1) slots = 1;
+  return static_cast<int>(slots);
+}
+
+int spff_conv3d_stem_fwd_stats(const float* x, const float* w, void* y, long long ldy, int cout, spff_shape s,
+                               float* stat_partial, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(x && w && y && stat_partial, "conv3d_stem_fwd_stats: null pointer");
+  SPFF_REQUIRE(cout == 32, "conv3d_stem_fwd_stats: cout must be 32 (got %d)", cout);
+  SPFF_REQUIRE(s.n > 0 && s.n <= 65535 && s.d > 0 && s.h > 0 && s.w > 0, "conv3d_stem_fwd_stats: bad shape");
+  dim3 grid(spff_conv3d_stem_stat_slots(s), s.n);
+  const size_t smem = (27 + 16) * cout * sizeof(float);
+  spff::stem_fwd_stats_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, w, static_cast<bf16*>(y), ldy, cout, s,
+                                                                                     stat_partial);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }

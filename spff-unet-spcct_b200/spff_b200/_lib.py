@@ -48,6 +48,8 @@ _PROTOTYPES = {
     "spff_conv3d_k3_wgrad_workspace": [c_int, c_int, Shape],
     "spff_conv3d_k3_wgrad": [_P, _LL, c_int, _P, _LL, c_int, Shape, _P, c_float, _P, c_size_t, _P],
     "spff_conv3d_stem_fwd": [_P, _P, _P, _LL, c_int, Shape, _P],
+    "spff_conv3d_stem_stat_slots": [Shape],
+    "spff_conv3d_stem_fwd_stats": [_P, _P, _P, _LL, c_int, Shape, _P, _P],
     "spff_conv3d_stem_wgrad_workspace": [c_int],
     "spff_conv3d_stem_wgrad": [_P, _P, _LL, c_int, Shape, _P, c_float, _P, c_size_t, _P],
     "spff_pack_convt_weight": [_P, _P, _P, c_int, c_int, _P],

@@ -89,7 +89,8 @@ class _Buffers:
                 if not (b == "enc1" and j == 1):
                     self.partial[f"{b}.{j}"] = torch.empty(n, self.slots[b], 2, c, device=device)
                 self.coef[f"{b}.{j}"] = torch.empty(n, c, 4, device=device)
-        self.stats1 = torch.zeros(n, self.C[1], 2, dtype=torch.float64, device=device)   # stem output (no conv epilogue)
+        self.stem_slots = ops.conv3d_stem_stat_slots(Shape(n, d, h, w))
+        self.partial["enc1.1"] = torch.empty(n, self.stem_slots, 2, self.C[1], device=device)
         # decoder output resampled to the caller's depth: the head's input
         self.hx = bf(d0, h, w, base) if d0 != d else None
         self._logits_shape = (n, k, d0, h, w)
@@ -176,7 +177,7 @@ class CicekEngine:
         self._bufs.clear()
 
     # ------------------------------------------------------------------------------------------
-    def _bn(self, B: _Buffers, b: str, j: int, training: bool, stats=None):
+    def _bn(self, B: _Buffers, b: str, j: int, training: bool):
         p, bufs = self._params(), self._buffers()
         l = _LEVEL[b]
         c = B.C[l]
@@ -185,7 +186,7 @@ class CicekEngine:
         rm, rv = bufs[f"{b}.{i}.running_mean"], bufs[f"{b}.{i}.running_var"]
         if training:
             ops.bn_coeffs(p[f"{b}.{i}.weight"], p[f"{b}.{i}.bias"], BN_EPS, B.n, c, dd * hh * ww, B.coef[f"{b}.{j}"],
-                          partial=None if stats is not None else B.partial[f"{b}.{j}"], slots=B.slots[b], stats=stats,
+                          partial=B.partial[f"{b}.{j}"], slots=B.stem_slots if (b == "enc1" and j == 1) else B.slots[b],
                           momentum=BN_MOMENTUM, running_mean=rm, running_var=rv)
             bufs[f"{b}.{i}.num_batches_tracked"].add_(1)
         else:
@@ -197,11 +198,11 @@ class CicekEngine:
         l = _LEVEL[b]
         cin, c = self.channels(b)
         if b == "enc1":
-            ops.conv3d_stem_fwd(x_img, p[f"{b}.0.weight"], B.x1[b], c)
             if training:
-                B.stats1.zero_()
-                ops.in_stats(B.x1[b], c, B.stats1)
-            self._bn(B, b, 1, training, stats=B.stats1 if training else None)
+                ops.conv3d_stem_fwd_stats(x_img, p[f"{b}.0.weight"], B.x1[b], c, B.partial[f"{b}.1"])
+            else:
+                ops.conv3d_stem_fwd(x_img, p[f"{b}.0.weight"], B.x1[b], c)
+            self._bn(B, b, 1, training)
         else:
             if training:
                 ops.conv3d_k3_fwd_stats(xin, cin, self._packed[f"{b}.1"][0], B.x1[b], c, B.partial[f"{b}.1"])

@@ -138,6 +138,8 @@ class _GroupBuffers:
             for j in (1, 2):
                 if not (b == "enc1" and j == 1):
                     self.partial[f"{b}.{j}"] = torch.empty(n, self.slots[b], 2, c, device=device)
+        self.stem_slots = ops.conv3d_stem_stat_slots(Shape(n, d, h, w))
+        self.partial["enc1.1"] = torch.empty(n, self.stem_slots, 2, f, device=device)
         self.f64.commit()
         self.f32.commit()
         self.coef = {f"{b}.{j}": torch.empty(n, self.C[_LEVEL[b]], 4, device=device) for b in BLOCKS for j in (1, 2)}
@@ -324,11 +326,10 @@ class SpffEngine:
         count = B.d * shp.h * shp.w
         # conv1 -> IN statistics -> a1 = lrelu(IN(x1))
         # (the tensor-core convs produce the InstanceNorm statistics in their epilogue; the stem needs a pass)
-        if b == "enc1":
-            ops.conv3d_stem_fwd(B.x_in, p[f"{b}.{cn1}.0.weight"], B.x1[b], c)
-            st1 = B.f64.get(B.idx[f"{b}.stats1"])
-            ops.in_stats(B.x1[b], c, st1)
-            ops.in_coeffs(st1, p[f"{b}.{cn1}.1.weight"], p[f"{b}.{cn1}.1.bias"], EPS, B.n, c, count, B.coef[f"{b}.1"])
+        if b == "enc1":   # the Cin = 1 stem takes its statistics in its own epilogue, like the tensor-core convs
+            ops.conv3d_stem_fwd_stats(B.x_in, p[f"{b}.{cn1}.0.weight"], B.x1[b], c, B.partial[f"{b}.1"])
+            ops.in_coeffs_from_partials(B.partial[f"{b}.1"], B.stem_slots, p[f"{b}.{cn1}.1.weight"], p[f"{b}.{cn1}.1.bias"],
+                                        EPS, B.n, c, count, B.coef[f"{b}.1"])
         else:
             ops.conv3d_k3_fwd_stats(xin, cin, self._packed[f"{b}.1"][0], B.x1[b], c, B.partial[f"{b}.1"])
             ops.in_coeffs_from_partials(B.partial[f"{b}.1"], B.slots[b], p[f"{b}.{cn1}.1.weight"], p[f"{b}.{cn1}.1.bias"],

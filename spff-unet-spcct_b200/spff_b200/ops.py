@@ -127,6 +127,19 @@ def conv3d_stem_fwd(x, w, y, cout):
     call("spff_conv3d_stem_fwd", ptr(x), ptr(w), ptr(y), ldy, cout, s, stream_ptr())
 
 
+def conv3d_stem_stat_slots(shape: Shape) -> int:
+    return int(_lib.lib.spff_conv3d_stem_stat_slots(shape))
+
+
+def conv3d_stem_fwd_stats(x, w, y, cout, partial):
+    """Stem forward + {sum, sum sq} partials of y (fp32 [n, slots, 2, cout], slots = conv3d_stem_stat_slots)."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 1
+    s, ldy = _view(y, cout)
+    assert partial.dtype == torch.float32 and partial.is_contiguous()
+    assert partial.numel() >= s.n * conv3d_stem_stat_slots(s) * 2 * cout
+    call("spff_conv3d_stem_fwd_stats", ptr(x), ptr(w), ptr(y), ldy, cout, s, ptr(partial), stream_ptr())
+
+
 def conv3d_stem_wgrad(x, dy, cout, dw, beta=0.0):
     s, lddy = _view(dy, cout)
     ws = workspace(int(_lib.lib.spff_conv3d_stem_wgrad_workspace(cout)), x.device)

@@ -273,6 +273,21 @@ def test_stem(n, d, h, w):
     assert rel(dw, refw) < 4e-3
     ops.conv3d_stem_wgrad(x, dyb, 32, dw, 1.0)
     assert rel(dw, 2 * refq) < 1e-4
+    # forward with the statistics taken in the epilogue: same output bits, partial sums = fp32 sums of the accumulators
+    from spff_b200._lib import Shape
+    slots = ops.conv3d_stem_stat_slots(Shape(n, d, h, w))
+    partial = torch.full((n, slots, 2, 32), float("nan"), device="cuda")
+    y2 = torch.full_like(y, float("nan"))
+    ops.conv3d_stem_fwd_stats(x, wt, y2, 32, partial)
+    assert torch.equal(y2, y)
+    tot = partial.double().sum(1)                       # [n, 2, 32]
+    assert float((tot[:, 0].float() - ref.sum(dim=(2, 3, 4))).abs().max()) < 1e-3 * float(ref.abs().sum(dim=(2, 3, 4)).max())
+    assert rel(tot[:, 1].float(), (ref * ref).sum(dim=(2, 3, 4))) < 1e-4
+    coef = torch.empty(n, 32, 4, device="cuda")
+    gamma, beta = torch.rand(32, device="cuda") + 0.5, torch.randn(32, device="cuda")
+    ops.in_coeffs_from_partials(partial, slots, gamma, beta, 1e-5, n, 32, d * h * w, coef)
+    assert torch.allclose(coef[..., 2], ref.mean(dim=(2, 3, 4)), atol=1e-4)
+    assert torch.allclose(coef[..., 3], 1.0 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5), rtol=1e-3)
 
 
 @pytest.mark.parametrize("n,d,h,w,cin,cout", [(2, 5, 8, 8, 64, 32), (1, 5, 4, 4, 128, 64), (1, 5, 2, 2, 256, 128),
