@@ -255,7 +255,8 @@ def run_b200(args):
     # ---- device-resident steps, with CUDA events around the conv3 launches (roofline) ----
     clocks = ClockSampler(local)
     clocks.start()
-    conv_names = {"spff_conv3d_k3_fwd", "spff_conv3d_k3_fwd_stats", "spff_conv3d_k3_dgrad", "spff_conv3d_k3_wgrad"}
+    conv_names = {"spff_conv3d_k3_fwd", "spff_conv3d_k3_fwd_stats", "spff_conv3d_k3_dgrad", "spff_conv3d_k3_dgrad_stats",
+                  "spff_conv3d_k3_wgrad"}
     prof = _lib.Profile(select=lambda n: n in conv_names)
     calls0 = _lib.CALLS
     _lib.PROFILE = prof
@@ -279,7 +280,8 @@ def run_b200(args):
         peaks, peak_kind = load_peaks()
         n_f, ms_f, fl_f = [a + b for a, b in zip(conv.get("spff_conv3d_k3_fwd", (0, 0.0, 0.0)),
                                                  conv.get("spff_conv3d_k3_fwd_stats", (0, 0.0, 0.0)))]
-        n_d, ms_d, fl_d = conv.get("spff_conv3d_k3_dgrad", (0, 0.0, 0.0))
+        n_d, ms_d, fl_d = [a + b for a, b in zip(conv.get("spff_conv3d_k3_dgrad", (0, 0.0, 0.0)),
+                                                 conv.get("spff_conv3d_k3_dgrad_stats", (0, 0.0, 0.0)))]
         n_w, ms_w, fl_w = conv.get("spff_conv3d_k3_wgrad", (0, 0.0, 0.0))
         ach = (fl_f + fl_d) / max(ms_f + ms_d, 1e-9) * 1e3 / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))

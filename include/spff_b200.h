@@ -79,6 +79,10 @@ int spff_conv3d_k3_fwd_stats(const void* x, long long ldx, int cin, const void* 
 /* dx = input gradient of the same convolution (ATen convolution_backward, grad_input). */
 int spff_conv3d_k3_dgrad(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
                          int cin, spff_shape s, void* stream);
+/* The same, plus the per-item column statistics of dx: stat_partial[n][slots][2][cin] as in spff_conv3d_k3_fwd_stats.
+ * Their sums over (n, slots) are the bias gradient of a ConvTranspose3d whose output dx is the gradient of. */
+int spff_conv3d_k3_dgrad_stats(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
+                               int cin, spff_shape s, float* stat_partial, void* stream);
 
 /* dw[cout][cin][3][3][3] (fp32) = beta*dw + weight gradient (ATen convolution_backward, grad_weight).
  * Split over positions; fp32 partial tiles go to `workspace` (size from the query below, which

@@ -640,4 +640,13 @@ int spff_conv3d_k3_dgrad(const void* dy, long long lddy, int cout, const void* w
   return conv3_common(dy, lddy, cout, w_dgrad, dx, lddx, cin, s, nullptr, stream, "conv3d_k3_dgrad");
 }
 
+/* dgrad that also writes the per-item column statistics of dx ({sum, sum of squares} per input channel, the layout of
+ * spff_conv3d_k3_fwd_stats): the column sums of a decoder block's input gradient are the bias gradient of the
+ * transposed conv that produced that input (models.py:668-672), so no separate pass over dx is needed. */
+int spff_conv3d_k3_dgrad_stats(const void* dy, long long lddy, int cout, const void* w_dgrad, void* dx, long long lddx,
+                               int cin, spff_shape s, float* stat_partial, void* stream) {
+  SPFF_REQUIRE(stat_partial, "conv3d_k3_dgrad_stats: null partial buffer");
+  return conv3_common(dy, lddy, cout, w_dgrad, dx, lddx, cin, s, stat_partial, stream, "conv3d_k3_dgrad_stats");
+}
+
 }  // extern "C"

@@ -45,6 +45,7 @@ _PROTOTYPES = {
     "spff_conv3d_k3_stat_slots": [Shape],
     "spff_conv3d_k3_fwd_stats": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P, _P],
     "spff_conv3d_k3_dgrad": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P],
+    "spff_conv3d_k3_dgrad_stats": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P, _P],
     "spff_conv3d_k3_wgrad_workspace": [c_int, c_int, Shape],
     "spff_conv3d_k3_wgrad": [_P, _LL, c_int, _P, _LL, c_int, Shape, _P, c_float, _P, c_size_t, _P],
     "spff_conv3d_stem_fwd": [_P, _P, _P, _LL, c_int, Shape, _P],

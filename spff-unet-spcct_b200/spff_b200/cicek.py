@@ -34,7 +34,7 @@ import torch
 
 from . import ops
 from ._lib import Shape
-from .engine import LossTally, _Pool
+from .engine import LossTally
 
 ENC = ("enc1", "enc2", "enc3", "enc4", "bott")
 DEC = ("dec4", "dec3", "dec2", "dec1")
@@ -105,9 +105,7 @@ class _Buffers:
             self.R = {f"{b}.{j}": torch.zeros(n, self.DHW[_LEVEL[b]][0], self.C[_LEVEL[b]], 6, device=device)
                       for b in BLOCKS for j in (1, 2)}
             self.bcoef = {f"{b}.{j}": torch.empty(n, self.C[_LEVEL[b]], 4, device=device) for b in BLOCKS for j in (1, 2)}
-            self.b64 = _Pool(torch.float64, device)
-            self.bidx = {up: self.b64.reserve(n, self.C[l], 2) for l, up, _, _ in _UPS}
-            self.b64.commit()
+            self.dpartial = {l: torch.empty(n, self.slots[dec], 2, 2 * self.C[l], device=device) for l, _, dec, _ in _UPS}
 
     def shape(self, level: int) -> Shape:
         return Shape(self.n, *self.DHW[level])
@@ -265,12 +263,14 @@ class CicekEngine:
             ops.conv3d_stem_wgrad(x_img, t1, c, G[f"{b}.0.weight"], 1.0)
         else:
             ops.conv3d_k3_wgrad(xin, cin, t1, c, G[f"{b}.0.weight"], 1.0)
-            ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.1"][1], dxin, cin)
+            if b.startswith("dec"):   # + column sums of the input gradient: the transposed conv's bias gradient
+                ops.conv3d_k3_dgrad_stats(t1, c, self._packed[f"{b}.1"][1], dxin, cin, B.dpartial[l])
+            else:
+                ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.1"][1], dxin, cin)
 
     def backward(self, B: _Buffers, G: Dict[str, torch.Tensor], x: torch.Tensor, ghead: torch.Tensor):
         """ghead: gradient w.r.t. the head's input (bf16 [n,d0,h,w,32]). Accumulates (+=) every parameter
         gradient except the head's into the fp32 tensors of `G`."""
-        B.b64.zero()
         if B.hx is not None:
             ops.depth_resample(ghead, B.gout[1], self.matrix(B.d, B.d0, x.device, transpose=True))
         elif ghead.data_ptr() != B.gout[1].data_ptr():
@@ -280,7 +280,6 @@ class CicekEngine:
             self._block_bwd(B, G, dec, B.gout[l], B.cat[l], B.dcat[l], None)
             dy = B.dcat[l][..., :cu]
             ops.convt_k222_wgrad(B.out[below], 2 * cu, dy, cu, G[f"{up}.weight"], 1.0)
-            ops.in_stats(dy, cu, B.b64.get(B.bidx[up]))
             ops.convt_k222_dgrad(dy, cu, self._packed[up][1], B.gout[l + 1], 2 * cu)
         self._block_bwd(B, G, "bott", B.gout[5], B.pool[4], B.dpool[4], None)
         x_img = B.x_in if B.x_in is not None else x
@@ -292,8 +291,8 @@ class CicekEngine:
                 self._block_bwd(B, G, enc, dskip, B.pool[l - 1], B.dpool[l - 1], None)
             else:
                 self._block_bwd(B, G, enc, dskip, None, None, x_img)
-        for _, up, _, _ in _UPS:   # ConvTranspose3d bias gradient = column sums of dy
-            G[f"{up}.bias"].add_(B.b64.get(B.bidx[up])[:, :, 0].sum(0).float())
+        for l, up, _, _ in _UPS:   # ConvTranspose3d bias gradient = column sums of dy (dgrad epilogue partials)
+            G[f"{up}.bias"].add_(B.dpartial[l][:, :, 0, :B.C[l]].double().sum((0, 1)).float())
 
     # ------------------------------------------------------------------------------------------
     def _check_input(self, x: torch.Tensor) -> torch.Tensor:

@@ -161,8 +161,10 @@ class _GroupBuffers:
                 c = self.C[_LEVEL[b]]
                 for j in (1, 2):
                     self.idx[f"{b}.R{j}"] = self.b32.reserve(n, d, c, 6)
-            for up, c in (("up3", self.C[3]), ("up2", self.C[2]), ("up1", self.C[1])):
-                self.idx[f"{up}.bstats"] = self.b64.reserve(n, c, 2)
+            # column statistics of a decoder block's input gradient (dgrad epilogue): their first C_l columns sum to the
+            # bias gradient of the transposed conv of that level
+            self.dpartial = {l: torch.empty(n, self.slots[dec], 2, 2 * self.C[l], device=device)
+                             for l, dec in ((3, "dec3"), (2, "dec2"), (1, "dec1"))}
             self.b32.commit()
             self.b64.commit()
             self.bcoef = {f"{b}.{j}": torch.empty(n, self.C[_LEVEL[b]], 4, device=device) for b in BLOCKS for j in (1, 2)}
@@ -413,7 +415,10 @@ class SpffEngine:
             ops.conv3d_stem_wgrad(B.x_in, t1, c, G[f"{b}.{cn1}.0.weight"], 1.0)
         else:
             ops.conv3d_k3_wgrad(xin, cin, t1, c, G[f"{b}.{cn1}.0.weight"], 1.0)
-            ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.1"][1], dxin, cin)
+            if b.startswith("dec"):
+                ops.conv3d_k3_dgrad_stats(t1, c, self._packed[f"{b}.1"][1], dxin, cin, B.dpartial[l])
+            else:
+                ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.1"][1], dxin, cin)
 
     def backward_group(self, B: _GroupBuffers, T: GateTables, G: Dict[str, torch.Tensor],
                        dlogits: Optional[torch.Tensor], after_decoder: Optional[Callable[[], None]] = None):
@@ -432,11 +437,9 @@ class SpffEngine:
             dy = B.dcat[l][..., :cu]
             xb = B.out[below]
             ops.convt_k122_wgrad(xb, 2 * cu, dy, cu, G[f"{up}.weight"], 1.0)
-            ops.in_stats(dy, cu, B.b64.get(B.idx[f"{up}.bstats"]))
             ops.convt_k122_dgrad(dy, cu, self._packed[up][1], B.gout[l + 1], 2 * cu)
         if after_decoder is not None:   # head / decoder / transposed-conv gradients of this group are complete
-            for up in ("up3", "up2", "up1"):
-                G[f"{up}.bias"].add_(B.b64.get(B.idx[f"{up}.bstats"])[:, :, 0].sum(0).float())
+            self._up_bias_grads(B, G)
             after_decoder()
         self._block_bwd(B, T, G, "bott", B.gout[4], B.pool[3], B.dpool[3])
         for l, enc in ((3, "enc3"), (2, "enc2"), (1, "enc1")):
@@ -447,10 +450,15 @@ class SpffEngine:
                 self._block_bwd(B, T, G, enc, dskip, B.pool[l - 1], B.dpool[l - 1])
             else:
                 self._block_bwd(B, T, G, enc, dskip, None, None)
-        # ConvTranspose3d bias gradient = column sums of dy (fp64 per-sample partials -> fp32 accumulate)
         if after_decoder is None:
-            for up in ("up3", "up2", "up1"):
-                G[f"{up}.bias"].add_(B.b64.get(B.idx[f"{up}.bstats"])[:, :, 0].sum(0).float())
+            self._up_bias_grads(B, G)
+
+    @staticmethod
+    def _up_bias_grads(B: _GroupBuffers, G: Dict[str, torch.Tensor]):
+        """ConvTranspose3d bias gradient = column sums of dy = the `up` half of the decoder input gradient, summed by the
+        dgrad epilogue per work item (fp32) and folded here in double."""
+        for l, up in ((3, "up3"), (2, "up2"), (1, "up1")):
+            G[f"{up}.bias"].add_(B.dpartial[l][:, :, 0, :B.C[l]].double().sum((0, 1)).float())
 
     # ------------------------------------------------------------------------------------------
     # batch-level drivers

@@ -81,6 +81,17 @@ def conv3d_k3_dgrad(dy, cout, w_dgrad, dx, cin):
     call("spff_conv3d_k3_dgrad", ptr(dy), lddy, cout, ptr(w_dgrad), ptr(dx), lddx, cin, s, stream_ptr())
 
 
+def conv3d_k3_dgrad_stats(dy, cout, w_dgrad, dx, cin, partial):
+    """dgrad + per-item {sum, sum sq} partials of dx (fp32 [n, slots, 2, cin])."""
+    s, lddy = _view(dy, cout)
+    s2, lddx = _view(dx, cin)
+    assert (s.n, s.d, s.h, s.w) == (s2.n, s2.d, s2.h, s2.w)
+    assert partial.dtype == torch.float32 and partial.is_contiguous()
+    assert partial.numel() >= s.n * conv3d_k3_stat_slots(s) * 2 * cin
+    _lib.NOTE = conv3_flops(s, cin, cout)
+    call("spff_conv3d_k3_dgrad_stats", ptr(dy), lddy, cout, ptr(w_dgrad), ptr(dx), lddx, cin, s, ptr(partial), stream_ptr())
+
+
 _WS = {}
 
 
