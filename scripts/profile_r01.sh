@@ -17,7 +17,7 @@ cap bwd_reduce4 norm_act_bwd_reduce4 0 2
 cap bwd_apply4 norm_act_bwd_apply4 0 2
 cap norm_act "^norm_act_kernel" 0 3
 cap norm_act_pool norm_act_pool_kernel 0 1
-cap head_loss head_loss_kernel 0 1
+cap head_loss head_loss 0 1
 cap maxpool_bwd maxpool_bwd_add 2 1
 cap wgrad32 "conv3_wgrad_kernel" 0 2
 cap stem "stem_" 0 2
