@@ -113,22 +113,30 @@ __global__ void __launch_bounds__(kBlock, 5) in_stats_kernel(const __nv_bfloat16
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (r < g.rpi) {
+    auto body = [&](const uint4& raw) {
+      float f[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] = fmaf(f[i], f[i], q[i]);
+      }
+    };
     constexpr int U = 4;   // independent 16-byte loads in flight per thread
-    for (int p = p0 + r; p < p1; p += U * g.rpi) {
+    int cnt = (p0 + r < p1) ? (p1 - p0 - r + g.rpi - 1) / g.rpi : 0;
+    const long long sx = static_cast<long long>(g.rpi) * ld;
+    const __nv_bfloat16* px = x + (base + p0 + r) * ld + v * 8;
+    for (; cnt >= U; cnt -= U) {
       uint4 raw[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        raw[u] = (p + u * g.rpi < p1) ? ldg16(x + (base + p + u * g.rpi) * ld + v * 8) : make_uint4(0, 0, 0, 0);
+      for (int u = 0; u < U; ++u) raw[u] = ldg16(px + u * sx);
+      px += U * sx;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float f[8];
-        unpack8(raw[u], f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s[i] += f[i];
-          q[i] = fmaf(f[i], f[i], q[i]);
-        }
-      }
+      for (int u = 0; u < U; ++u) body(raw[u]);
+    }
+    for (; cnt > 0; --cnt) {
+      body(ldg16(px));
+      px += sx;
     }
   }
   float sq[16];
@@ -519,16 +527,31 @@ maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ dpool, long long ldp, c
   const int p0 = blockIdx.x * g.chunk;
   const int p1 = min(g.hw, p0 + g.chunk);
   if (r >= g.rpi) return;
+  // (hp, wp) of the pooled position advance incrementally; the four window corners sit at fixed element offsets
+  int hp = (p0 + r) / w2, wp = (p0 + r) % w2;
+  const int dh = g.rpi / w2, dw = g.rpi % w2;
+  const long long oy[4] = {0, ldy, static_cast<long long>(w) * ldy, static_cast<long long>(w + 1) * ldy};
+  const long long od[4] = {0, ldd, static_cast<long long>(w) * ldd, static_cast<long long>(w + 1) * ldd};
+  const __nv_bfloat16* yb = y + base * ldy + v * 8;
+  __nv_bfloat16* db = dskip + base * ldd + v * 8;
+  const __nv_bfloat16* pp = dpool + (basep + p0 + r) * ldp + v * 8;
+  const long long sp = static_cast<long long>(g.rpi) * ldp;
   for (int p = p0 + r; p < p1; p += g.rpi) {
-    const int hp = p / w2, wp = p % w2;
+    const long long corner = static_cast<long long>(2 * hp) * w + 2 * wp;
+    const __nv_bfloat16* yc = yb + corner * ldy;
+    __nv_bfloat16* dc = db + corner * ldd;
     float gp[8], yv[4][8];
-    unpack8(ldg16(dpool + (basep + p) * ldp + v * 8), gp);
-    long long pos[4];
+    uint4 raw[4], rawd[4];
+    const uint4 rawg = ldg16(pp);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      pos[k] = base + static_cast<long long>(2 * hp + (k >> 1)) * w + 2 * wp + (k & 1);
-      unpack8(ldg16(y + pos[k] * ldy + v * 8), yv[k]);
+    for (int k = 0; k < 4; ++k) raw[k] = ldg16(yc + oy[k]);
+    if (accumulate) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rawd[k] = *reinterpret_cast<const uint4*>(dc + od[k]);
     }
+    unpack8(rawg, gp);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) unpack8(raw[k], yv[k]);
     int arg[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -546,14 +569,21 @@ maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ dpool, long long ldp, c
     for (int k = 0; k < 4; ++k) {
       float o[8];
       if (accumulate) {
-        unpack8(*reinterpret_cast<const uint4*>(dskip + pos[k] * ldd + v * 8), o);
+        unpack8(rawd[k], o);
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] += (arg[i] == k) ? gp[i] : 0.f;
-      stg16(dskip + pos[k] * ldd + v * 8, pack8(o));
+      stg16(dc + od[k], pack8(o));
+    }
+    pp += sp;
+    hp += dh;
+    wp += dw;
+    if (wp >= w2) {
+      wp -= w2;
+      ++hp;
     }
   }
 }
