@@ -92,9 +92,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 with open(f"profiles/{TAG}_bandwidth_kernels_ncu_full.md", "w") as f:
     f.write("# Round 1 — `ncu --set full --clock-control none --import-source on` captures of the bandwidth kernels\n\n"
             "Command: `SPFF_BENCH_SAMPLES=256 python bench.py --steps 1 --warmup 3 --no-cpu`; first launches of each kernel in a step "
-            "(level-1 tensors: 256 slices x 5 x 128 x 128 positions x 32 channels bf16 = 1.342 GB each). Times under ncu are cold-cache; "
-            "`dram__bytes_write` includes the write-back of lines ncu's save/restore between replay passes left dirty (kernels that write "
-            f"almost nothing show GBs), so the read side is the one to compare with the algorithmic bytes. HBM peak (measured copy): {PEAK_HBM:.0f} GB/s.\n\n")
+            "(level-1 tensors: 256 slices x 5 x 128 x 128 positions x 32 channels bf16 = 1.342 GB each). Times under ncu are cold-cache and "
+            "serialised; mind the unit printed beside each metric (reads of the reduce kernels are GB, their writes MB). "
+            f"HBM peak (measured copy): {PEAK_HBM:.0f} GB/s.\n\n")
     for name in ("bwd_reduce4", "bwd_apply4", "norm_act", "norm_act_pool", "maxpool_bwd", "wgrad32", "stem", "head_loss"):
         path = f"{OUT}/prof_{name}_{TAG}.ncu-rep"
         try:
