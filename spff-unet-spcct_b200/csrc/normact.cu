@@ -309,6 +309,61 @@ norm_act_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float*
   }
 }
 
+// S[n][d][c] = sum_hw lrelu(x*A+B) alone (the gate statistic pass): the loop shape of in_stats_kernel — strided
+// pointers, U independent loads issued before the first use, a tail of single rows — which the generic kernel above
+// does not get from the compiler for its read-only variant (5.1 TB/s; this one is measured in DESIGN.md).
+__global__ void __launch_bounds__(kBlock, 4)
+norm_act_sum_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ coef, float* __restrict__ S,
+                    PlaneGrid g, int d, int c, float slope, float* __restrict__ part) {
+  extern __shared__ float red[];
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
+  const long long base = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  float A[8], B[8], acc[8];
+  load_ab(coef, n, c, v, A, B);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (r < g.rpi) {
+    auto body = [&](const uint4& raw) {
+      float f[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float z = fmaf(f[i], A[i], B[i]);
+        acc[i] += z > 0.f ? z : z * slope;
+      }
+    };
+    constexpr int U = 4;
+    int cnt = (p0 + r < p1) ? (p1 - p0 - r + g.rpi - 1) / g.rpi : 0;
+    const long long sx = static_cast<long long>(g.rpi) * ldx;
+    const __nv_bfloat16* px = x + (base + p0 + r) * ldx + v * 8;
+    for (; cnt >= U; cnt -= U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) raw[u] = ldg16(px + u * sx);
+      px += U * sx;
+#pragma unroll
+      for (int u = 0; u < U; ++u) body(raw[u]);
+    }
+    for (; cnt > 0; --cnt) {
+      body(ldg16(px));
+      px += sx;
+    }
+  }
+  reduce_rows_fast<8>(acc, red, g.c8);     // c8 is a power of two <= 32 here (host dispatch)
+  const int L = g.c8 < 32 ? g.c8 : 32;
+  if (threadIdx.x < L * 8) {
+    const float t = reduce_rows_fetch<8>(red, g.c8, threadIdx.x);
+    const long long plane = static_cast<long long>(n) * d + dd;
+    if (part)
+      part[(plane * gridDim.x + blockIdx.x) * c + threadIdx.x] = t;
+    else
+      atomicAdd(S + plane * c + threadIdx.x, t);
+  }
+}
+
 // out = lrelu(x*A+B)*P+Q written at full resolution AND its (1,2,2) max-pool. A thread owns the
 // 2x2 window of one pooled position. grid = (chunks over pooled positions, d, n). h, w even.
 template <bool AFFINE>
@@ -1050,8 +1105,12 @@ int spff_norm_act_reduce(const void* x, long long ldx, const float* coef, float*
   const size_t need = spff_norm_act_reduce_workspace(c, s);
   float* part = (workspace && need > 0 && workspace_bytes >= need) ? static_cast<float*>(workspace) : nullptr;
   SPFF_REQUIRE(!workspace || part, "norm_act_reduce: workspace too small or channel count without a fixed-order path");
-  spff::norm_act_kernel<false, true, false><<<grid, kBlock, 8 * kBlock * sizeof(float), st>>>(
-      static_cast<const bf16*>(x), ldx, coef, nullptr, nullptr, nullptr, 0, S, g, s.d, c, slope, part);
+  if (spff::fast_reduce_ok_host(g.c8))
+    spff::norm_act_sum_kernel<<<grid, kBlock, 8 * kBlock * sizeof(float), st>>>(static_cast<const bf16*>(x), ldx, coef, S, g,
+                                                                              s.d, c, slope, part);
+  else
+    spff::norm_act_kernel<false, true, false><<<grid, kBlock, 8 * kBlock * sizeof(float), st>>>(
+        static_cast<const bf16*>(x), ldx, coef, nullptr, nullptr, nullptr, 0, S, g, s.d, c, slope, part);
   if (part) {
     const long long total = static_cast<long long>(s.n) * s.d * c;
     spff::sum_chunks_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(part, grid.x, c, 1, S, 1, 0, 1, total);
