@@ -129,7 +129,7 @@ stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_b
 // writes one partial row partial[n][slot][2][cout] = {sum, sum of squares} — the layout of the tensor-core conv's
 // epilogue partials, reduced in a fixed order by spff_in_coeffs_from_partials / spff_bn_coeffs. Replaces the
 // separate spff_in_stats pass over the stem output.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)   // <= 128 registers: two resident blocks (152 and one block without the cap)
 stem_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
                       int cout, spff_shape s, float* __restrict__ partial) {
   extern __shared__ float sw[];  // [27][cout], then [8 warps][2][cout] for the block reduction
