@@ -32,6 +32,8 @@ struct PwParams {
   int scale;             // 2 forward (rows scatter to 2h+i, 2w+j), 1 dgrad
   int dscale;            // output planes per input plane: 2 for the (2,2,2) forward (plane 2d + (q >> 2)), else 1
   int nfull, noff;       // rows of one packed weight block and the first row this launch reads (N-split of wide outputs)
+  int nfold;             // forward: output quadrants folded into one MMA tile (N_mma = nfold * N <= 256): the position tile
+                         // is loaded once for all of them instead of once per quadrant
   const float* bias;     // [N] or null
 };
 
@@ -89,11 +91,12 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long items = p.ntiles * p.nquad;
+  const int ngroups = p.nquad / p.nfold;            // quadrant groups per position tile
+  const long long items = p.ntiles * ngroups;
   const int rows = p.bw * p.bh;
   auto decode = [&](long long item, int& qo, int& w0, int& h0, int& dd, int& n) {
-    qo = static_cast<int>(item % p.nquad);
-    long long t = item / p.nquad;
+    qo = static_cast<int>(item % ngroups) * p.nfold;   // first quadrant of the group
+    long long t = item / ngroups;
     w0 = static_cast<int>(t % p.tiles_w) * p.bw;
     t /= p.tiles_w;
     h0 = static_cast<int>(t % p.tiles_h) * p.bh;
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
     {
       int s = 0;
       uint32_t ph = 0;
-      const uint32_t bytes = rows * KC * 2 + p.N * KC * 2;
+      const uint32_t bytes = rows * KC * 2 + p.nfold * p.N * KC * 2;
       for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         int qo, w0, h0, dd, n;
         decode(item, qo, w0, h0, dd, n);
@@ -115,11 +118,13 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
           for (int kc = 0; kc < p.nkc; ++kc) {
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* st = smem + s * L::kStage;
-            const int blk = (p.nquad > 1 ? qo : t) * p.nkc + kc;
             if (leader) {
               mbar_expect_tx(&full[s], bytes);
               tma_load_5d(st, &maps.a[t], &full[s], kc * KC, w0, h0, dd, n);
-              tma_load_2d(st + L::kABytes, &maps.b, &full[s], 0, blk * p.nfull + p.noff);
+              for (int f = 0; f < p.nfold; ++f) {
+                const int blk = (p.nquad > 1 ? qo + f : t) * p.nkc + kc;
+                tma_load_2d(st + L::kABytes + f * p.N * KC * 2, &maps.b, &full[s], 0, blk * p.nfull + p.noff);
+              }
             }
             if (++s == L::kStages) {
               s = 0;
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
       constexpr uint32_t kSwz = (KC == 64) ? kSwizzle128 : kSwizzle64;
       constexpr uint32_t kSbo = (KC == 64) ? 1024 : 512;
       const uint64_t desc_hi = make_smem_desc_hi(16, kSbo, kSwz);
-      const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
+      const uint32_t idesc = make_idesc_bf16(128, p.nfold * p.N, 0, 0);
       const uint64_t desc0 = smem_desc(desc_hi, smem_u32(smem));
       int s = 0;
       uint32_t ph = 0, accph = 0;
@@ -175,36 +180,39 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
       decode(item, qo, w0, h0, dd, n);
       const int ww = w0 + m % p.bw, hh = h0 + m / p.bw;
       const bool ok = m < rows && ww < p.w && hh < p.h;
-      const int oh = hh * p.scale + (p.nquad > 1 ? ((qo >> 1) & 1) : 0);
-      const int ow = ww * p.scale + (p.nquad > 1 ? (qo & 1) : 0);
-      const int od = dd * p.dscale + (p.nquad > 4 ? (qo >> 2) : 0);
-      __nv_bfloat16* dst =
-          p.out + (((static_cast<long long>(n) * p.d * p.dscale + od) * p.ho + oh) * p.wo + ow) * p.ldo;
       mbar_wait(&acc_full[buf], (accph >> buf) & 1u);
       accph ^= 1u << buf;
       tc_fence_after();
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * 256 + c0, v);
-        tmem_ld_wait();
-        if (c0 + 32 >= p.N) {  // last chunk read: the MMA warp may reuse this accumulator
-          tc_fence_before();
-          mbar_arrive(&acc_empty[buf]);
-        }
-        if (ok) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
-            if (p.bias) {
-              a += __ldg(p.bias + p.noff + c0 + c);
-              b += __ldg(p.bias + p.noff + c0 + c + 1);
-            }
-            pk[c >> 1] = pack_bf16x2(a, b);
+      for (int f = 0; f < p.nfold; ++f) {
+        const int q = qo + f;
+        const int oh = hh * p.scale + (p.nquad > 1 ? ((q >> 1) & 1) : 0);
+        const int ow = ww * p.scale + (p.nquad > 1 ? (q & 1) : 0);
+        const int od = dd * p.dscale + (p.nquad > 4 ? (q >> 2) : 0);
+        __nv_bfloat16* dst =
+            p.out + (((static_cast<long long>(n) * p.d * p.dscale + od) * p.ho + oh) * p.wo + ow) * p.ldo;
+        for (int c0 = 0; c0 < p.N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * 256 + f * p.N + c0, v);
+          tmem_ld_wait();
+          if (f + 1 == p.nfold && c0 + 32 >= p.N) {  // last chunk read: the MMA warp may reuse this accumulator
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
           }
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+          if (ok) {
+            uint32_t pk[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) d4[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            for (int c = 0; c < 32; c += 2) {
+              float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
+              if (p.bias) {
+                a += __ldg(p.bias + p.noff + c0 + c);
+                b += __ldg(p.bias + p.noff + c0 + c + 1);
+              }
+              pk[c >> 1] = pack_bf16x2(a, b);
+            }
+            uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) d4[qq] = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+          }
         }
       }
       buf ^= 1;
@@ -260,7 +268,7 @@ int launch_pw(const PwMaps& maps, const PwParams& p, cudaStream_t st) {
     SPFF_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal + 1024));
     attr_set = true;
   }
-  long long items = p.ntiles * p.nquad;
+  long long items = p.ntiles * (p.nquad / p.nfold);
   int ctas = debug_ctas() > 0 ? debug_ctas() : num_sms();
   if (items < ctas) ctas = static_cast<int>(items);
   pw_gemm_kernel<KC><<<ctas, kThreads, L::kTotal + 1024, st>>>(maps, p);
@@ -553,6 +561,8 @@ int convt_fwd_impl(const void* x, long long ldx, int cin, const void* w_fwd, con
   const int nc = pick_nchunk(cout);
   e = encode_b_map(&maps.b, w_fwd, KC, static_cast<long long>(nq) * p.nkc * cout, nc);
   if (e) return e;
+  p.nfold = 1;
+  while (p.nfold * 2 <= nq && p.nfold * 2 * nc <= 256 && !debug_flag(5)) p.nfold *= 2;   // test hook: key 5 disables folding
   for (int noff = 0; noff < cout; noff += nc) {
     p.N = nc; p.noff = noff;
     p.out = static_cast<__nv_bfloat16*>(y) + noff;
@@ -567,7 +577,7 @@ int convt_dgrad_impl(const void* dy, long long lddy, int cout, const void* w_dgr
   const int KC = conv3_kc(cout), nq = 4 * nd;
   PwParams p{};
   fill_tiles(&p, s);
-  p.nkc = cout / KC; p.ntap = nq; p.nquad = 1; p.nfull = cin;
+  p.nkc = cout / KC; p.ntap = nq; p.nquad = 1; p.nfull = cin; p.nfold = 1;
   p.ldo = lddx; p.ho = s.h; p.wo = s.w; p.scale = 1; p.dscale = 1; p.bias = nullptr;
   PwMaps maps;
   int e;
