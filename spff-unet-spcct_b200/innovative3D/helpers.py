@@ -96,10 +96,9 @@ def masked_ce_loss(logits, labels, ignore_index=255):
     class_weights None and no voxel weights (models.py:779-798). Shares the tally pass with the metrics."""
     ign = _NO_IGNORE if ignore_index is None else int(ignore_index)
     t = _tally(logits, labels, ign)
-    if getattr(t, "_clamped", None) is None:
-        t._clamped = LossTally(t.k, t.nll.device)
-        t._clamped.nll, t._clamped.count, t._clamped.confusion = t.nll, t.count.clamp(min=1), t.confusion
-    return _CrossEntropyFn.apply(logits, labels, ign, t._clamped)
+    clamped = LossTally.__new__(LossTally)           # same statistics, denominator clamped like .clamp_min(1.0)
+    clamped.k, clamped.nll, clamped.count, clamped.confusion = t.k, t.nll, t.count.clamp(min=1), t.confusion
+    return _CrossEntropyFn.apply(logits, labels, ign, clamped)
 
 
 def _dice_from_tally(t: LossTally, smooth: float) -> torch.Tensor:

@@ -554,6 +554,45 @@ class BaseLitModel(pl.LightningModule):
         """Gradient views (by core parameter name) of the last fit_step."""
         return self._fused["G"]
 
+    def fused_optimizer_state(self) -> Dict[str, object]:
+        """State of the fused Adam (first / second moments over the flat parameter buffer, step count, current lr and
+        the plateau scheduler) for checkpoint / resume — what `optimizer.state_dict()` holds on the Lightning path.
+        Save it next to `state_dict()`."""
+        st = self._fused
+        if st is None:
+            return {"step": 0}
+        out = {"step": int(st["step"]), "exp_avg": st["m"].detach().cpu(), "exp_avg_sq": st["v"].detach().cpu(),
+               "lr": float(self.hparams.lr)}
+        pl_ = getattr(self, "_plateau", None)
+        if pl_ is not None:
+            out["plateau"] = dict(vars(pl_))
+        return out
+
+    def load_fused_optimizer_state(self, state: Dict[str, object]) -> None:
+        """Inverse of `fused_optimizer_state` (call after `load_state_dict`, on the device the model trains on)."""
+        core = self.model
+        core.materialize(self._frames_of(core))
+        if not state or int(state.get("step", 0)) == 0:
+            self._fused = None
+            return
+        flat = core._flat
+        if state["exp_avg"].numel() != flat.numel():
+            raise ValueError(f"optimizer state holds {state['exp_avg'].numel()} elements, the model {flat.numel()}")
+        self._fused = dict(flat=flat, grad=torch.zeros_like(flat), m=state["exp_avg"].to(flat), v=state["exp_avg_sq"].to(flat),
+                           step=int(state["step"]), tally=LossTally(self.hparams.num_classes, flat.device))
+        self._fused["G"] = core._views(self._fused["grad"])
+        self.hparams["lr"] = float(state.get("lr", self.hparams.lr))
+        if "plateau" in state:
+            self._plateau = PlateauLR(float(self.hparams.lr), mode="max", factor=0.5, patience=5)
+            vars(self._plateau).update(state["plateau"])
+
+    @staticmethod
+    def _frames_of(core) -> int:
+        for m in core.modules():
+            if isinstance(m, FourierGate3D) and m._mask is not None:
+                return 2 * (m._mask.shape[2] - 1) + 1
+        return NUM_FRAMES
+
     def step_metrics(self, tally: LossTally, total_voxels: int):
         """per_class_metrics_3d's 9-tuple from a fit_step tally (one device->host copy)."""
         return metrics_from_confusion(tally.confusion.cpu().numpy(), total_voxels)
@@ -928,6 +967,27 @@ class LitCicek3DUNet_DepthAdapter_Published(pl.LightningModule):
 
     def fused_grads(self) -> Dict[str, torch.Tensor]:
         return self._fused["G"]
+
+    def fused_optimizer_state(self) -> Dict[str, object]:
+        """Momentum buffer + step count of the fused SGD, for checkpoint / resume (save next to `state_dict()`)."""
+        st = self._fused
+        if st is None:
+            return {"step": 0}
+        return {"step": int(st["step"]), "momentum_buffer": st["buf"].detach().cpu(), "lr": float(self.hparams.lr)}
+
+    def load_fused_optimizer_state(self, state: Dict[str, object]) -> None:
+        net = self.backbone
+        net.materialize()
+        if not state or int(state.get("step", 0)) == 0:
+            self._fused = None
+            return
+        flat = net._flat
+        if state["momentum_buffer"].numel() != flat.numel():
+            raise ValueError(f"optimizer state holds {state['momentum_buffer'].numel()} elements, the model {flat.numel()}")
+        self._fused = dict(flat=flat, grad=torch.zeros_like(flat), buf=state["momentum_buffer"].to(flat), step=int(state["step"]),
+                           tally=LossTally(self.hparams.num_classes, flat.device))
+        self._fused["G"] = net._views(self._fused["grad"])
+        self.hparams["lr"] = float(state.get("lr", self.hparams.lr))
 
     @torch.no_grad()
     def predict_labels(self, x) -> torch.Tensor:
