@@ -119,7 +119,6 @@ class _GroupBuffers:
         self.x1, self.a1, self.x2, self.out = {}, {}, {}, {}
         self.partial: Dict[str, torch.Tensor] = {}
         self.slots: Dict[str, int] = {}
-        self.f64 = _Pool(torch.float64, device)
         self.f32 = _Pool(torch.float32, device)
         self.idx: Dict[str, int] = {}
         for b in BLOCKS:
@@ -130,8 +129,6 @@ class _GroupBuffers:
             self.a1[b] = bf(hh, ww, c)
             self.x2[b] = bf(hh, ww, c)
             self.out[b] = self.cat[l][..., c:] if b.startswith("enc") else bf(hh, ww, c)
-            for j in (1, 2):
-                self.idx[f"{b}.stats{j}"] = self.f64.reserve(n, c, 2)
             self.idx[f"{b}.S"] = self.f32.reserve(n, d, c)
             # per-item partial statistics written by the conv epilogue (no zeroing needed)
             self.slots[b] = ops.conv3d_k3_stat_slots(Shape(n, d, hh, ww))
@@ -140,7 +137,6 @@ class _GroupBuffers:
                     self.partial[f"{b}.{j}"] = torch.empty(n, self.slots[b], 2, c, device=device)
         self.stem_slots = ops.conv3d_stem_stat_slots(Shape(n, d, h, w))
         self.partial["enc1.1"] = torch.empty(n, self.stem_slots, 2, f, device=device)
-        self.f64.commit()
         self.f32.commit()
         self.coef = {f"{b}.{j}": torch.empty(n, self.C[_LEVEL[b]], 4, device=device) for b in BLOCKS for j in (1, 2)}
         self.P = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
@@ -156,7 +152,6 @@ class _GroupBuffers:
             self.t2 = {l: bf(*self.HW[l], self.C[l]) for l in (1, 2, 3, 4)}
             self.dpool = {l: bf(*self.HW[l + 1], self.C[l]) for l in (1, 2, 3)}
             self.b32 = _Pool(torch.float32, device)
-            self.b64 = _Pool(torch.float64, device)
             for b in BLOCKS:
                 c = self.C[_LEVEL[b]]
                 for j in (1, 2):
@@ -166,7 +161,6 @@ class _GroupBuffers:
             self.dpartial = {l: torch.empty(n, self.slots[dec], 2, 2 * self.C[l], device=device)
                              for l, dec in ((3, "dec3"), (2, "dec2"), (1, "dec1"))}
             self.b32.commit()
-            self.b64.commit()
             self.bcoef = {f"{b}.{j}": torch.empty(n, self.C[_LEVEL[b]], 4, device=device) for b in BLOCKS for j in (1, 2)}
             self.dSa = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
             self.Pout = {b: torch.empty(n, d, self.C[_LEVEL[b]], device=device) for b in BLOCKS}
@@ -356,7 +350,6 @@ class SpffEngine:
         B.logits), "argmax" (uint8 label map [n,d,h,w] into labels_out) or "none"."""
         p = self.params()
         B.x_in = x
-        B.f64.zero()
         B.f32.zero()
         self._block_fwd(B, T, "enc1", None, B.pool[1])
         self._block_fwd(B, T, "enc2", B.pool[1], B.pool[2])
@@ -427,7 +420,6 @@ class SpffEngine:
         kernel already left the head's input gradient in B.gout[1] (and its dW/db in G)."""
         p = self.params()
         B.b32.zero()
-        B.b64.zero()
         if dlogits is not None:
             ops.head_bwd(dlogits, B.out["dec1"], p["out.weight"], B.gout[1], G["out.weight"].view(-1, self.cfg.base),
                          G["out.bias"], 1.0)
