@@ -62,3 +62,31 @@ def test_grid_boundaries_ragged():
     from innovative3D.datasets import _grid_boundaries
     assert _grid_boundaries(512, 5) == [0, 102, 204, 307, 409, 512]     # the example in datasets.py:57
     assert _grid_boundaries(7, 3) == DO.grid_boundaries(7, 3)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_host_index_tables_random_draws_match_the_oracle(seed):
+    """Many random decision sequences (flips, rot90, jitter, stripe shuffle with random grid sizes, ragged stripes):
+    gathering with this tree's index tables == the oracle's tensor-by-tensor TrainGridAug on the same `random` stream."""
+    from innovative3D.datasets import TrainGridAug
+    rng = random.Random(seed)
+    square = seed % 3 != 0
+    h = rng.choice([24, 40, 56, 64])
+    w = h if square else rng.choice([16, 48, 72])
+    gs = rng.choice([None, 1, 2, 3, 4, 5, 7])
+    x, y = DO.aug_input(500 + seed, 3, h, w)
+    kw = dict(noise_p=0.0, rot90_p=0.5 if square else 0.0)
+    random.seed(9000 + seed)
+    xo, yo = DO.train_grid_aug(x.clone(), y.clone(), gs, **kw)
+    nxt = random.random()
+    random.seed(9000 + seed)
+    m, scale, shift, noise, stamp = TrainGridAug(**kw)._draw(h, w, gs)
+    assert random.random() == nxt
+    hh, ww = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    u, v = (ww, hh) if m.t else (hh, ww)
+    xs = x.numpy()[0][:, m.a[u], m.b[v]]
+    if not (scale == 1.0 and shift == 0.0):
+        xs = (xs * np.float32(scale)).astype(np.float32) + np.float32(shift)
+    if stamp:
+        xs[0, :32, :32] = xs[0, :32, :32].max() + np.float32(max(np.abs(xs).max(), np.float32(1.0))) * np.float32(0.25)
+    assert np.array_equal(xs.astype(np.float32), xo.numpy()[0]) and np.array_equal(y.numpy()[:, m.a[u], m.b[v]], yo.numpy())
