@@ -59,7 +59,7 @@ struct SmemLayout {
   static constexpr int kOffA = 0;
   static constexpr int kOffW = kOffA + kStages * kABytes;
   static constexpr int kOffX = kOffW + kWStages * kWBytes;          // epilogue exchange rows
-  static constexpr int kXBytes = 2 * 4 * 2 * kCoBlk * 4;
+  static constexpr int kXBytes = 2 * 4 * 2 * kCoBlk * 4 + 2 * kCoBlk * 4;   // + one all-zero row pair (ALIGNED tile edges)
   static constexpr int kOffS = kOffX + kXBytes;                     // STATS: per-warp column sums [4][2][32]
   static constexpr int kSBytes = 4 * 2 * kCoBlk * 4;
   static constexpr int kOffBar = kOffS + kSBytes;
@@ -91,7 +91,11 @@ __device__ __forceinline__ void warp_column_sums(float (&a)[32], int lane) {
 // squares per output channel, fp32 values before the bf16 rounding) as one partial row per work
 // item - no atomics, reduced in a fixed order by spff_in_coeffs_from_partials. This removes the
 // separate statistics pass over the freshly written conv output.
-template <int KC, bool RES, bool STATS>
+// ALIGNED: the tile is a whole number of image rows starting at a multiple of 32 positions (W in {32, 64, 128}, no halo)
+// and every tile row is a real position. An image-row edge can then only fall between lane 31 and lane 0, so the
+// per-element "has a left / right neighbour" selects and the row mask of the statistics disappear: the warp that
+// hands a boundary value to its neighbour through shared memory writes zeros when that neighbour sits across an edge.
+template <int KC, bool RES, bool STATS, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const FpropParams p) {
@@ -102,6 +106,8 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint8_t* sW = smem + L::kOffW;
   float* sX = reinterpret_cast<float*>(smem + L::kOffX);
   float* sS = reinterpret_cast<float*>(smem + L::kOffS);
+  float* sZero = sX + 2 * 4 * 2 * kCoBlk;   // 2 x kCoBlk zeros (visible after the set-up __syncthreads)
+  if (threadIdx.x < 2 * kCoBlk) sZero[threadIdx.x] = 0.f;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBar);
   uint64_t* full = bars;
   uint64_t* empty = bars + L::kStages;
@@ -378,21 +384,29 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         // rows m-1 / m+1 live in the neighbouring lanes; across warps they go through smem
         float4* xrow = reinterpret_cast<float4*>(sX + (xpar * 4 + warp) * 2 * kCoBlk);
         if (lane == 31) {
+          const bool keep = !ALIGNED || has_right;   // ALIGNED: the receiver (row m+1) starts an image row -> zeros
 #pragma unroll
           for (int v = 0; v < 8; ++v)
-            xrow[v] = make_float4(__uint_as_float(t0[4 * v]), __uint_as_float(t0[4 * v + 1]),
-                                  __uint_as_float(t0[4 * v + 2]), __uint_as_float(t0[4 * v + 3]));
+            xrow[v] = keep ? make_float4(__uint_as_float(t0[4 * v]), __uint_as_float(t0[4 * v + 1]),
+                                         __uint_as_float(t0[4 * v + 2]), __uint_as_float(t0[4 * v + 3]))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (lane == 0) {
+          const bool keep = !ALIGNED || has_left;    // ALIGNED: the receiver (row m-1) ends an image row -> zeros
 #pragma unroll
           for (int v = 0; v < 8; ++v)
-            xrow[8 + v] = make_float4(__uint_as_float(t2[4 * v]), __uint_as_float(t2[4 * v + 1]),
-                                      __uint_as_float(t2[4 * v + 2]), __uint_as_float(t2[4 * v + 3]));
+            xrow[8 + v] = keep ? make_float4(__uint_as_float(t2[4 * v]), __uint_as_float(t2[4 * v + 1]),
+                                             __uint_as_float(t2[4 * v + 2]), __uint_as_float(t2[4 * v + 3]))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         named_bar_sync(1, 128);
         const float4* lrow = reinterpret_cast<const float4*>(sX + (xpar * 4 + (warp > 0 ? warp - 1 : 0)) * 2 * kCoBlk);
         const float4* rrow =
             reinterpret_cast<const float4*>(sX + (xpar * 4 + (warp < 3 ? warp + 1 : 3)) * 2 * kCoBlk + kCoBlk);
+        if (ALIGNED) {   // the tile's first / last row has no neighbour inside the tile: an image-row edge
+          if (warp == 0) lrow = reinterpret_cast<const float4*>(sZero);
+          if (warp == 3) rrow = reinterpret_cast<const float4*>(sZero + kCoBlk);
+        }
         uint32_t packed[16];
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
@@ -408,11 +422,19 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             float r = __shfl_down_sync(0xffffffffu, __uint_as_float(t2[c]), 1);
             l = (lane == 0) ? lb[e] : l;
             r = (lane == 31) ? rb[e] : r;
-            v[e] = __uint_as_float(t1[c]) + (has_left ? l : 0.f) + (has_right ? r : 0.f);
-            if constexpr (STATS) {
-              const float vm = v[e] * rowmask;
-              ssum[c] += vm;
-              ssq[c] = fmaf(vm, v[e], ssq[c]);
+            if (ALIGNED) {
+              v[e] = __uint_as_float(t1[c]) + l + r;
+              if constexpr (STATS) {
+                ssum[c] += v[e];
+                ssq[c] = fmaf(v[e], v[e], ssq[c]);
+              }
+            } else {
+              v[e] = __uint_as_float(t1[c]) + (has_left ? l : 0.f) + (has_right ? r : 0.f);
+              if constexpr (STATS) {
+                const float vm = v[e] * rowmask;
+                ssum[c] += vm;
+                ssq[c] = fmaf(vm, v[e], ssq[c]);
+              }
             }
           }
           packed[2 * c4] = pack_bf16x2(v[0], v[1]);
@@ -454,8 +476,8 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   }
 }
 
-template <int KC, bool RES, bool STATS>
-int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y, long long ldy, int cout,
+template <int KC, bool RES, bool STATS, bool ALIGNED>
+int launch_fprop_impl(const void* x, long long ldx, int cin, const void* wpk, void* y, long long ldy, int cout,
                  spff_shape s, float* stat_partial, cudaStream_t stream) {
   using L = SmemLayout<KC, RES>;
   FpropParams p;
@@ -503,7 +525,7 @@ int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SPFF_CUDA(cudaFuncSetAttribute(conv3_fprop_kernel<KC, RES, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPFF_CUDA(cudaFuncSetAttribute(conv3_fprop_kernel<KC, RES, STATS, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    L::kTotal + 1024));
     attr_set = true;
   }
@@ -517,9 +539,19 @@ int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y
   } else if (p.items < ctas) {
     ctas = static_cast<int>(p.items);
   }
-  conv3_fprop_kernel<KC, RES, STATS><<<ctas, kThreads, L::kTotal + 1024, stream>>>(tx, tw, p);
+  conv3_fprop_kernel<KC, RES, STATS, ALIGNED><<<ctas, kThreads, L::kTotal + 1024, stream>>>(tx, tw, p);
   SPFF_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int KC, bool RES, bool STATS>
+int launch_fprop(const void* x, long long ldx, int cin, const void* wpk, void* y, long long ldy, int cout,
+                 spff_shape s, float* stat_partial, cudaStream_t stream) {
+  // whole image rows per tile, 32-aligned, no partial tile (see the ALIGNED note at the kernel)
+  const long long hw = static_cast<long long>(s.h) * s.w;
+  const bool aligned = (kTileM % s.w == 0) && (s.w % 32 == 0) && (hw % kTileM == 0) && !debug_flag(6);
+  if (aligned) return launch_fprop_impl<KC, RES, STATS, true>(x, ldx, cin, wpk, y, ldy, cout, s, stat_partial, stream);
+  return launch_fprop_impl<KC, RES, STATS, false>(x, ldx, cin, wpk, y, ldy, cout, s, stat_partial, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
