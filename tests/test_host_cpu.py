@@ -149,3 +149,30 @@ def test_plateau_lr_matches_torch_scheduler():
         sch.step(v)
         assert mine.step(v) == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12, abs=0)
     assert mine.lr < 1e-4
+
+
+def test_sample_group_sizing(monkeypatch):
+    """SpffEngine.fit_group: the largest group <= the request whose buffers fit in 45 % of the free HBM
+    (26.5 level-1 tensors per slice for a training step, 16.7 for inference)."""
+    from spff_b200.engine import SpffEngine
+    free = 170 * 2 ** 30
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda device=None: (free, 183 * 2 ** 30))
+    # the bench slices (5 x 128 x 128): 139 MB per slice for training -> the requested 256 fits
+    assert SpffEngine.fit_group(256, 5, 128, 128, "cuda:0", train=True) == 256
+    # native 512 x 512 slices: 2.2 GB per slice for training, 1.4 GB for inference
+    per_train = 26.5 * 5 * 512 * 512 * 64
+    assert SpffEngine.fit_group(256, 5, 512, 512, "cuda:0", train=True) == int(0.45 * free / per_train) == 36
+    assert SpffEngine.fit_group(256, 5, 512, 512, "cuda:0", train=False) == int(0.45 * free / (16.7 * 5 * 512 * 512 * 64)) == 58
+    assert SpffEngine.fit_group(8, 5, 512, 512, "cuda:0", train=True) == 8
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda device=None: (2 ** 30, 183 * 2 ** 30))
+    assert SpffEngine.fit_group(256, 5, 512, 512, "cuda:0", train=True) == 1      # never below one slice
+    assert SpffEngine._groups(10, 4) == [(0, 4), (4, 8), (8, 10)]                  # ragged last group
+
+
+def test_depth_matrix_matches_interpolate():
+    """spff_b200.cicek.depth_matrix == F.interpolate(mode='trilinear', align_corners=False) along D (models.py:153-163)."""
+    from spff_b200.cicek import depth_matrix
+    for din, dout in ((5, 16), (16, 5), (3, 16), (16, 16), (7, 4)):
+        eye = torch.eye(din).reshape(din, 1, din, 1, 1)
+        ref = torch.nn.functional.interpolate(eye, size=(dout, 1, 1), mode="trilinear", align_corners=False)
+        assert torch.allclose(depth_matrix(din, dout), ref.reshape(din, dout).t(), atol=1e-6), (din, dout)
