@@ -3,7 +3,7 @@ and the ROI rasteriser at 5 x 512 x 512. Prints algorithmic GB/s (bytes read + w
 import os, random, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "spff-unet-spcct_b200")]
-from innovative3D.datasets import TrainGridAug, rasterize_roi_labels
+from innovative3D.datapath_gpu import TrainGridAug, rasterize_roi_labels
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 x = torch.randn(n, 1, 5, 128, 128, device="cuda")
 y = torch.randint(0, 13, (n, 5, 128, 128), device="cuda")

@@ -23,13 +23,20 @@ int check_cuda(cudaError_t e, const char* what) {
   return SPFF_ERR_CUDA;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
 int num_sms() {
-  static int cached = 0;
-  if (cached) return cached;
+  static int cached[kMaxDevices] = {};   // per device: one process may drive several GPUs
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const int slot = (dev >= 0 && dev < kMaxDevices) ? dev : kMaxDevices - 1;
+  if (cached[slot]) return cached[slot];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  cached[slot] = n;
   return n;
 }
 

@@ -14,6 +14,9 @@ namespace spff {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+// index of the current CUDA device, clamped to [0, kMaxDevices) - key of the per-device caches
+constexpr int kMaxDevices = 64;
+int current_device();
 // test hook (spff_debug_set key 0): CTA count override for persistent kernels, 0 = one per SM
 int debug_ctas();
 // test hook (spff_debug_set key >= 1): generic integer flags, 0 by default. key 1: disable the all-kh wgrad variant

@@ -523,7 +523,8 @@ int launch_fprop_impl(const void* x, long long ldx, int cin, const void* wpk, vo
     int e = encode_tmap_bf16(&tw, wpk, 2, dims, str, box, KC * 2);
     if (e) return e;
   }
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the opt-in is per device (and per template instance)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     SPFF_CUDA(cudaFuncSetAttribute(conv3_fprop_kernel<KC, RES, STATS, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    L::kTotal + 1024));

@@ -587,7 +587,8 @@ int launch_wgrad(const void* x, long long ldx, int cin, const void* dy, long lon
     int e = encode_tmap_bf16(&tx, x, 5, dims, str, box, CIB * 2);
     if (e) return e;
   }
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the opt-in is per device (and per template instance)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     SPFF_CUDA(cudaFuncSetAttribute(conv3_wgrad_kernel<COB, CIB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    C::Total + 1024));
@@ -626,7 +627,8 @@ int launch_wgrad_kh(const void* x, long long ldx, int cin, const void* dy, long 
     int e = encode_tmap_bf16(&tx, x, 5, dims, str, box, 64);
     if (e) return e;
   }
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the opt-in is per device (and per template instance)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     SPFF_CUDA(cudaFuncSetAttribute(conv3_wgrad_kh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::Total + 1024));
     attr_set = true;

@@ -263,7 +263,8 @@ int encode_grid_map(CUtensorMap* m, const void* base, long long ld, int c, int n
 template <int KC>
 int launch_pw(const PwMaps& maps, const PwParams& p, cudaStream_t st) {
   using L = PwSmem<KC>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the opt-in is per device (and per template instance)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     SPFF_CUDA(cudaFuncSetAttribute(pw_gemm_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal + 1024));
     attr_set = true;
@@ -505,7 +506,8 @@ PwWgPlan make_pw_plan(int cin, int cout, spff_shape s) {
 template <int COB, int CIB>
 int launch_pw_wgrad(const PwWgMaps& maps, const PwWgParams& p, int ctas, cudaStream_t st) {
   using C = PwWgCfg<COB, CIB>;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};   // the opt-in is per device (and per template instance)
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     SPFF_CUDA(cudaFuncSetAttribute(pw_wgrad_kernel<COB, CIB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    C::Total + 1024));

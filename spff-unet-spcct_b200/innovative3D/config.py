@@ -4,10 +4,15 @@ Mirrors the part of the reference's `innovative3D/config.py` that the callers of
 import (`train.py:64-78,89`, `test.py:62-72`): the label space, the training constants
 (config.py:21-33) and `VARIANTS` — a list of `(name, zero-arg builder, DataModule, ckpt_dir)`
 (config.py:271-280) whose builders construct the Lightning modules of `innovative3D.models`
-(config.py:410-476). Dataset geometry (ROI tables, DICOM roots, config.py:36-124) is outside the
-hot path and not restated here; unlike the reference, importing this module creates no directories
-under a hard-coded home path (config.py:15-19) — only CHECKPOINT_DIR / LOG_DIR, both overridable
-through the same environment variables (config.py:252-253).
+(config.py:410-476). Dataset geometry (ROI tables, DICOM roots, `dataset_configs`, `trainval_sets`,
+`test_set`, the VMI switches: config.py:36-124, 232-248) is the data layer's and is NOT restated here:
+any name this module does not define is handed through to the reference's `config.py` when a
+reference checkout is on `sys.path` (`_fallthrough.py`), so `train.py:64-78`, `test.py:62-72` and the
+reference's `datasets.py:24-35` import what they need from `innovative3D.config` unchanged. Without a
+reference checkout the three dataset lists read as empty lists and other data-layer names raise
+AttributeError. Unlike the reference, importing this module creates no directories under a hard-coded
+home path (config.py:15-19) — only CHECKPOINT_DIR / LOG_DIR are used, both overridable through the same
+environment variables (config.py:252-253).
 """
 import inspect
 import os
@@ -36,12 +41,6 @@ label_colors = {
     11: (0, 128, 128), 12: (128, 128, 0),
 }
 
-# Dataset selection lives with the data pipeline (out of scope); callers that import these names get
-# empty lists unless a data layer fills them.
-dataset_configs = []
-trainval_sets = []
-test_set = []
-
 LOSS_NAME = "ce_plus_macro_dice"
 FOCAL_ALPHA, FOCAL_GAMMA, GRAD_WEIGHT = 0.25, 2.0, 1.0
 USE_VMI = False
@@ -52,15 +51,24 @@ LOG_DIR = Path(os.getenv("LOG_DIR", str(_PROJECT_ROOT / "runs"))).resolve()
 CKPT_DIR = CHECKPOINT_DIR
 
 
-def MultiDicomDataModule3D(*args, **kwargs):
-    """The reference's DICOM data module (datasets.py:280-364) is the caller's side of the
-    boundary; resolve it lazily from whatever `innovative3D.datasets` is importable."""
-    try:
-        mod = import_module("innovative3D.datasets")
-    except ImportError as e:  # pragma: no cover - data layer is out of scope here
-        raise ImportError("innovative3D.datasets (the reference's CPU data pipeline) is not part of the B200 hot "
-                          "path; install the reference's data layer next to this package to train on DICOM data") from e
-    return mod.MultiDicomDataModule3D(*args, **kwargs)
+def _data_module(name):
+    """The reference's DICOM data modules (datasets.py:280-364, 367-422) are the caller's side of the boundary:
+    `innovative3D.datasets` is not a module of this tree, it resolves to the reference checkout's file through the
+    extended package path (`__init__.py`), exactly like config.py:130-142 resolves it lazily."""
+    def factory(*args, **kwargs):
+        try:
+            mod = import_module("innovative3D.datasets")
+        except ImportError as e:
+            raise ImportError("innovative3D.datasets (the reference's CPU data pipeline: DICOM ingest, DataModules) is "
+                              "outside the B200 hot path and not part of this tree; run with the reference checkout on "
+                              "sys.path (e.g. from its directory) so that its datasets.py is found") from e
+        return getattr(mod, name)(*args, **kwargs)
+    factory.__name__ = factory.__qualname__ = name
+    return factory
+
+
+MultiDicomDataModule3D = _data_module("MultiDicomDataModule3D")
+MultiDicomDataModule2D = _data_module("MultiDicomDataModule2D")
 
 
 def build_class(class_name: str, **ctor_kwargs):
@@ -113,5 +121,42 @@ def make_cicek_depth_adapter_sgd_wce():
 
 _add_variant("3DUNet", make_cicek_depth_adapter_sgd_wce, MultiDicomDataModule3D, CHECKPOINT_DIR / "3DUNet")   # config.py:306-311
 
+B200_VARIANT_NAMES = [v[0] for v in VARIANTS]     # the variants that run on the B200 kernels
+
+
+def _append_reference_variants():
+    """The reference registers four more model families (UNETR, SwinUNETR, R2U-Net, ResUNet++: config.py:316-391). They are
+    outside the hot path; when a reference checkout is on sys.path their registry entries are kept, unchanged, after
+    the B200 ones (their builders resolve `innovative3D.models.<Class>` through this tree's models.py to the reference's
+    own PyTorch code), so `train.py:1615-1618` still loops over every variant."""
+    from ._fallthrough import reference_module
+    try:
+        ref = reference_module("config")
+    except Exception as e:   # a broken / partial checkout must not take the hot path down with it
+        import warnings
+        warnings.warn(f"innovative3D.config: reference config.py found but not importable ({e!r}); "
+                      "only the B200 variants are registered")
+        return
+    if ref is not None:
+        for v in getattr(ref, "VARIANTS", []):
+            if v[0] not in B200_VARIANT_NAMES:
+                VARIANTS.append(v)
+
+
+_append_reference_variants()
 VARIANT_NAMES = [v[0] for v in VARIANTS]
 SELECTED_VARIANT = os.getenv("INNOVATIVE3D_VARIANT")
+
+
+from ._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+_ref_getattr = _module_getattr(__name__, "config", "dataset tables and data-layer switches live in the reference's config.py")
+
+
+def __getattr__(name):
+    try:
+        return _ref_getattr(name)
+    except AttributeError:
+        if name in ("dataset_configs", "trainval_sets", "test_set"):   # no data layer on the path: nothing to train on
+            return []
+        raise

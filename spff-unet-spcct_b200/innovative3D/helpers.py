@@ -182,3 +182,11 @@ LOSS_REGISTRY = {
     "ce_plus_macro_dice": lambda logits, labels, nc, ignore_index: ce_plus_macro_dice_loss(
         logits, labels, nc, ignore_index=ignore_index),
 }
+
+
+# Everything else of the reference's helpers.py (DICOM ingest, legacy augmentation, visualisers, unused losses:
+# helpers.py:43-662, 811-943) is outside the hot path; those names resolve to the reference's module when a reference
+# checkout is on sys.path, so `innovative3D/datasets.py:31-34` of the reference imports them from here unchanged.
+from ._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__, "helpers", "only the loss / step-metric functions of the hot path are rebuilt here")

@@ -19,6 +19,7 @@ LitSPCT_SEspec ("SP_UNet", depth padded 5 -> 16), LitSPCT_ControlUNet ("PlainCor
 """
 from __future__ import annotations
 
+import copy
 import os
 from typing import Dict, List, Optional
 
@@ -255,6 +256,21 @@ class UNet3D_SpectralCore(nn.Module):
         self._flat_numel = 0
         self._n_eager = 0     # elements of the flat buffer that existed before any lazy registration
 
+    def __deepcopy__(self, memo):
+        """`copy.deepcopy(core)` (train.py:1288 copies the core for its compute read-out; EMA / SWA helpers do the same):
+        parameters are cloned, the engine, the flat buffer and its views are NOT shared — the copy rebuilds them at its
+        first forward."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        lazy = {"_engine": None, "_flat": None, "_param_objs": {}, "_param_data": {}, "_copy_stream": None,
+                "_names": [], "_slots": {}, "_flat_numel": 0, "_n_eager": 0}
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = copy.deepcopy(lazy[k]) if k in lazy else copy.deepcopy(v, memo)
+        for m in new.modules():      # the two names of a lazy mask must stay ONE parameter in the copy
+            if isinstance(m, FourierGate3D) and "freq_mask" in m._parameters:
+                m._mask = m._parameters["freq_mask"]
+        return new
+
     # -- structure -----------------------------------------------------------------------------
     def net_config(self) -> NetConfig:
         blk = self.enc1
@@ -411,6 +427,15 @@ class BaseLitModel(pl.LightningModule):
         self.save_hyperparameters({"num_classes": num_classes, "lr": float(lr), "is_3d": bool(is_3d), **kwargs})
         self._fused = None
         self._copy_stream = None
+
+    def __deepcopy__(self, memo):
+        """The fused optimizer state, the copy stream and the trainer back-reference stay with the original."""
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        drop = {"_fused": None, "_copy_stream": None, "trainer": None, "_trainer": None}
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = drop[k] if k in drop else copy.deepcopy(v, memo)
+        return new
 
     def _normalize_input(self, x):
         return _pick_first_if_seq(x)
@@ -998,3 +1023,11 @@ class LitCicek3DUNet_DepthAdapter_Published(pl.LightningModule):
         net = self.backbone
         net.materialize()
         return net.engine.infer(x.to(net._flat.device), self.target_depth, training=net.training, argmax=True)
+
+
+# Model families outside the hot path (UNETR / SwinUNETR wrappers, R2U-Net, ResUNet++, their helper blocks and losses:
+# reference models.py:254-462, 858-1412) are not rebuilt: a name this module does not define resolves to the reference's
+# own PyTorch implementation when a reference checkout is on sys.path, so the other `config.VARIANTS` entries keep working.
+from ._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__, "models", "only the SPCT family and the 3DUNet control run on the B200 kernels")

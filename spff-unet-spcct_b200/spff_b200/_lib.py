@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -156,9 +157,42 @@ PROFILE = None   # set to a Profile() to time calls
 NOTE = None      # algorithmic work of the next call
 
 
+# Device of the tensor arguments of the call being assembled (per thread): `ptr()` records it, `stream_ptr()` hands out THAT device's
+# current stream, `call()` makes it the current CUDA device around the C call (kernel launches and TMA descriptors are
+# issued against the current device) and forgets it. Tensors of two devices in one call are an error.
+_TLS = threading.local()     # forward runs on the main thread, backward on autograd's worker thread
+
+
+def _enter_device():
+    """(device index or None, previous device index or None) for the call being issued."""
+    dev = getattr(_TLS, "dev", None)
+    _TLS.dev = None
+    if dev is None:
+        return None
+    import torch
+
+    cur = torch.cuda.current_device()
+    if cur == dev:
+        return None
+    torch.cuda.set_device(dev)
+    return cur
+
+
 def call(name: str, *args) -> None:
     global CALLS, NOTE
     CALLS += 1
+    prev = _enter_device()
+    try:
+        _call(name, *args)
+    finally:
+        if prev is not None:
+            import torch
+
+            torch.cuda.set_device(prev)
+
+
+def _call(name: str, *args) -> None:
+    global NOTE
     prof = PROFILE
     if prof is not None and (prof.select is None or prof.select(name)):
         import torch
@@ -177,13 +211,22 @@ def call(name: str, *args) -> None:
 
 
 def ptr(t) -> c_void_p:
-    """Device pointer of a torch tensor (or None)."""
+    """Device pointer of a torch tensor (or None). Records the tensor's device for the call being assembled."""
     if t is None:
         return c_void_p(0)
+    d = t.device
+    if d.type == "cuda":
+        seen = getattr(_TLS, "dev", None)
+        if seen is None:
+            _TLS.dev = d.index
+        elif seen != d.index:
+            _TLS.dev = None
+            raise RuntimeError(f"libspff_b200: tensors of one call live on different devices (cuda:{seen} and cuda:{d.index})")
     return c_void_p(t.data_ptr())
 
 
 def stream_ptr() -> c_void_p:
+    """Current stream of the device the call's tensors live on (not of whatever device happens to be current)."""
     import torch
 
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch.cuda.current_stream(getattr(_TLS, "dev", None)).cuda_stream)

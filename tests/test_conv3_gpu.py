@@ -38,6 +38,14 @@ CASES = [
     (1, 7, 8, 8, 32, 32),     # two plane groups
     (3, 5, 32, 32, 32, 32),
     (1, 5, 4, 4, 256, 256),
+    # the bench's level-1 / level-2 shapes: ALIGNED epilogue at 1 (W=128) and 2 (W=64) image rows per tile, resident
+    # (cin <= 64) and streamed weights, and more work items than persistent CTAs (a CTA loops over several items)
+    (2, 5, 128, 128, 32, 32),
+    (3, 5, 64, 64, 32, 64),
+    (2, 5, 64, 64, 64, 64),
+    (2, 5, 128, 128, 64, 32),
+    (2, 5, 64, 64, 128, 64),
+    (5, 5, 32, 32, 128, 128),
 ]
 
 
@@ -61,7 +69,7 @@ def test_conv3_fwd(n, d, h, w, cin, cout):
     assert (got - ref).abs().max() <= ref.abs().max() * 2 ** -7
 
 
-@pytest.mark.parametrize("n,d,h,w,cin,cout", CASES[:7])
+@pytest.mark.parametrize("n,d,h,w,cin,cout", CASES[:7] + CASES[10:])
 def test_conv3_dgrad(n, d, h, w, cin, cout):
     from spff_b200 import ops
 
@@ -109,6 +117,15 @@ WG_CASES = [
     (1, 7, 8, 8, 32, 32),
     (2, 5, 2, 2, 256, 256),
     (3, 5, 32, 32, 32, 32),
+    # the bench's level-1 / level-2 / level-3 plane sizes
+    (2, 5, 128, 128, 32, 32),
+    (2, 5, 128, 128, 64, 32),
+    (3, 5, 64, 64, 32, 64),
+    (2, 5, 64, 64, 64, 64),
+    (2, 5, 64, 64, 128, 64),
+    (5, 5, 32, 32, 128, 128),
+    (4, 5, 32, 32, 256, 128),
+    (6, 5, 16, 16, 256, 256),
 ]
 
 

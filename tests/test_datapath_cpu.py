@@ -40,7 +40,7 @@ def test_oracle_roi_labels_match_reference(name):
 @pytest.mark.parametrize("name", AUG)
 def test_host_index_tables_reproduce_the_reference(name):
     """TrainGridAug._draw (this tree): same `random` draws, and gathering with its tables == the reference's output."""
-    from innovative3D.datasets import TrainGridAug
+    from innovative3D.datapath_gpu import TrainGridAug
     seed, f, h, w, gs = _case(name)
     x, y = DO.aug_input(seed, f, h, w)
     aug = TrainGridAug(noise_p=0.0, rot90_p=0.5 if h == w else 0.0)
@@ -59,7 +59,7 @@ def test_host_index_tables_reproduce_the_reference(name):
 
 
 def test_grid_boundaries_ragged():
-    from innovative3D.datasets import _grid_boundaries
+    from innovative3D.datapath_gpu import _grid_boundaries
     assert _grid_boundaries(512, 5) == [0, 102, 204, 307, 409, 512]     # the example in datasets.py:57
     assert _grid_boundaries(7, 3) == DO.grid_boundaries(7, 3)
 
@@ -68,7 +68,7 @@ def test_grid_boundaries_ragged():
 def test_host_index_tables_random_draws_match_the_oracle(seed):
     """Many random decision sequences (flips, rot90, jitter, stripe shuffle with random grid sizes, ragged stripes):
     gathering with this tree's index tables == the oracle's tensor-by-tensor TrainGridAug on the same `random` stream."""
-    from innovative3D.datasets import TrainGridAug
+    from innovative3D.datapath_gpu import TrainGridAug
     rng = random.Random(seed)
     square = seed % 3 != 0
     h = rng.choice([24, 40, 56, 64])

@@ -1,4 +1,4 @@
-"""GPU: the data-path kernels (spff_roi_labels, spff_grid_aug) through innovative3D.datasets of this tree against the
+"""GPU: the data-path kernels (spff_roi_labels, spff_grid_aug) through innovative3D.datapath_gpu of this tree against the
 reference fixtures (tests/golden/datapath.npz) and the CPU oracle — bit-exact for labels, indices, jitter and stamp;
 the Gaussian noise (a different generator) statistically."""
 import os
@@ -17,7 +17,7 @@ ROI = sorted({k.split("_")[0] for k in GOLD.files if k.startswith("roi")})
 
 @pytest.mark.parametrize("name", AUG)
 def test_aug_matches_reference_fixture(name):
-    from innovative3D.datasets import TrainGridAug
+    from innovative3D.datapath_gpu import TrainGridAug
     from oracle import datapath_oracle as DO
     seed, f, h, w, gs = [int(v) for v in GOLD[name + "_case"]]
     gs = None if gs < 0 else gs
@@ -33,7 +33,7 @@ def test_aug_matches_reference_fixture(name):
 @pytest.mark.parametrize("labels_dtype", [torch.int64, torch.uint8])
 def test_aug_batch_equals_oracle_sample_by_sample(labels_dtype):
     """A batch of native-size slices: sample i of the batched device call == the i-th oracle call on the same `random` stream."""
-    from innovative3D.datasets import TrainGridAug
+    from innovative3D.datapath_gpu import TrainGridAug
     from oracle import datapath_oracle as DO
     bsz, f, h, w = 6, 5, 512, 512
     xs, ys = zip(*[DO.aug_input(50 + i, f, h, w) for i in range(bsz)])
@@ -51,7 +51,7 @@ def test_aug_batch_equals_oracle_sample_by_sample(labels_dtype):
 
 
 def test_aug_noise_statistics():
-    from innovative3D.datasets import TrainGridAug
+    from innovative3D.datapath_gpu import TrainGridAug
     torch.manual_seed(0)
     x = torch.randn(4, 1, 5, 128, 128, device="cuda") * 2.0
     aug = TrainGridAug(p_grid=0.0, flip_p=0.0, rot90_p=0.0, jitter_p=0.0, noise_p=1.0, noise_std=0.01)
@@ -71,7 +71,7 @@ def test_aug_noise_statistics():
 
 @pytest.mark.parametrize("name", ROI)
 def test_roi_labels_match_reference_fixture(name):
-    from innovative3D.datasets import rasterize_roi_labels
+    from innovative3D.datapath_gpu import rasterize_roi_labels
     rois = [tuple(int(v) for v in r) for r in GOLD[name + "_rois"]]
     want = GOLD[name + "_labels"]
     got = rasterize_roi_labels(rois, want.shape[0], want.shape[1], want.shape[2])
@@ -79,7 +79,7 @@ def test_roi_labels_match_reference_fixture(name):
 
 
 def test_roi_labels_native_size_equal_oracle_and_errors():
-    from innovative3D.datasets import rasterize_roi_labels, scaled_rois
+    from innovative3D.datapath_gpu import rasterize_roi_labels, scaled_rois
     from oracle import datapath_oracle as DO
     cfg = {"offset": (10, -5), "original_rois": [(200, 220, 160, 150, "c1"), (500, 300, 170, 165, "c2"), (820, 760, 140, 160, "c3"),
                                                  (420, 640, 150, 150, "c4"), (640, 900, 155, 145, "c5"), (480, 310, 80, 300, "c6")]}

@@ -48,7 +48,8 @@ def test_variants_registry_surface():
     names = [v[0] for v in C.VARIANTS]
     assert names[:1] == ["SPFF-UNet"] and {"E_SP_UNet", "FG_SP_UNet", "SP_UNet", "PlainCore_UNet", "3DUNet"} <= set(names)
     assert (C.NUM_CLASSES, C.NUM_FRAMES, C.IGNORE_INDEX, C.BATCH_SIZE, C.BEST_LR, C.SEEDS) == (13, 5, 255, 1, 1e-4, [42, 123, 999])
-    for name, builder, dm, ckpt in C.VARIANTS:
+    assert names[:6] == C.B200_VARIANT_NAMES     # the reference's other families (if a checkout is on the path) come after
+    for name, builder, dm, ckpt in C.VARIANTS[:6]:
         lit = builder()
         assert hasattr(lit, "model") and lit.hparams.num_classes == 13 and callable(dm)
         opt = lit.configure_optimizers()

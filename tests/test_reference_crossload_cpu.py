@@ -79,7 +79,7 @@ def test_train_py_builder_loop_on_this_trees_variants():
                     continue
             raise
 
-    for name, builder, dm, ckpt in C.VARIANTS:
+    for name, builder, dm, ckpt in C.VARIANTS[:len(C.B200_VARIANT_NAMES)]:     # the B200 variants; the rest are the reference's own
         lit = build_lit(builder)
         assert lit.hparams.num_classes == C.NUM_CLASSES and hasattr(lit, "training_step") and hasattr(lit, "configure_optimizers")
         assert hasattr(lit, "model") and isinstance(lit.model, torch.nn.Module)
