@@ -132,8 +132,14 @@ def test_trained_weights_meet_north_star_tolerances(variant):
     losses = _train(lit, 80, 8, 32, 32, 1e-3)
     assert losses[-1] < 0.6 * losses[0], losses[::10]
     sd = {k: v.detach().cpu().clone() for k, v in lit.state_dict().items() if not k.endswith("fgate._mask")}
-    x, lab = O.phantom_batch(2, 128, 128, seed=999, ignore_frac=0.01)
-    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd, x, lab, variant)
+    x, lab = O.phantom_batch(16, 128, 128, seed=999, ignore_frac=0.01)      # the bench's slice size
+    q = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    taps = {}
+    ref_logits = O.unet_forward(q, x, variant, taps)
+    ref_loss_t = O.ce_plus_macro_dice_loss(ref_logits, lab, 13)
+    ref_loss_t.backward()
+    ref_loss, ref_logits = float(ref_loss_t.detach()), ref_logits.detach()
+    ref_grads = {k: v.grad for k, v in q.items()}
     xg, lg = x.cuda(), lab.cuda()
     logits = lit(xg)
     assert rel(logits, ref_logits) < 2e-2
@@ -146,6 +152,18 @@ def test_trained_weights_meet_north_star_tolerances(variant):
     loss = lit.compute_loss(logits, lg)
     assert abs(float(loss) - ref_loss) < 2e-2 * max(1.0, abs(ref_loss))
     loss.backward()
+    # per-layer activations on the trained weights: every block output <= 2e-2
+    B = lit.model.engine.buffers(16, 5, 128, 128, torch.device("cuda", torch.cuda.current_device()), train=False)
+    with torch.no_grad():
+        lit.model.sample_group, keep = 16, lit.model.sample_group
+        lit(xg)
+        lit.model.sample_group = keep
+    acts = {n: rel(B.out[n].permute(0, 4, 1, 2, 3), t) for n, t in taps.items()}
+    print("block activations", {k: round(v, 4) for k, v in acts.items()})
+    assert max(acts.values()) < 2e-2, acts
+    # per-layer parameter gradients: north_star's 2e-2 on EVERY parameter (conv, norm, transposed conv, head, SE, EFiLM
+    # MLP, FourierGate scalars), the 16x16 bottleneck included. (A parameter gradient sums over positions, so its bf16
+    # noise falls with the batch: 2.6 % on bott.* at 2 slices, 1.8 % at 8, 0.6 % at configs[0]'s 128.)
     worst = {}
     for k, p in lit.model.named_parameters():
         k = k.replace("fgate._mask", "fgate.freq_mask")
@@ -153,22 +171,8 @@ def test_trained_weights_meet_north_star_tolerances(variant):
         if float(r.norm()) < 1e-6:
             continue
         worst[k] = rel(p.grad, r)
-    big = {k: v for k, v in worst.items() if k.endswith(".0.weight") or k.endswith(".1.weight") or k.startswith("out") or k.startswith("up")}
     print(sorted(worst.items(), key=lambda kv: -kv[1])[:8])
-    # 2e-2 everywhere except the 16x16 bottleneck (and the transposed conv / SE fed by it), where bf16 storage
-    # alone costs 2-3 %: PyTorch's own CPU bf16 autocast of the oracle on such weights measures 2.5-3.0 % on
-    # bott.* / up3 / se.2-3 and a 1.7 % median over all conv weights - this path
-    # measures 2.0-2.4 % there and < 1.6 % elsewhere.
-    deep = lambda k: k.startswith("bott.") or k.startswith("up3") or k.startswith("se.")
-    shallow = {k: v for k, v in big.items() if not deep(k)}
-    assert max(shallow.values()) < 2e-2, sorted(shallow.items(), key=lambda kv: -kv[1])[:5]
-    assert max(big.values()) < 3e-2, sorted(big.items(), key=lambda kv: -kv[1])[:5]
-    # every other parameter: 5e-2; the 1- and 3-element FourierGate scalars are sums with heavy cancellation: 0.15
-    sizes = {k.replace("fgate._mask", "fgate.freq_mask"): p.numel() for k, p in lit.model.named_parameters()}
-    rest = {k: v for k, v in worst.items() if sizes[k] >= 16}
-    tiny = {k: v for k, v in worst.items() if sizes[k] < 16}
-    assert max(rest.values()) < 5e-2, sorted(rest.items(), key=lambda kv: -kv[1])[:5]
-    assert not tiny or max(tiny.values()) < 0.15, sorted(tiny.items(), key=lambda kv: -kv[1])[:5]
+    assert max(worst.values()) < 2e-2, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
 
 
 def test_config1_batch_against_oracle():
@@ -197,7 +201,9 @@ def test_config1_batch_against_oracle():
 
 
 def test_taps_per_block_activations():
-    """Per-block outputs (encoder skips, bottleneck, decoders) vs the oracle's taps on fixture weights."""
+    """Per-block outputs (encoder skips, bottleneck, decoders) vs the oracle's taps on UNTRAINED name-seeded weights (a 4x4
+    bottleneck on random weights: the 2e-2 bound on trained weights is asserted in
+    test_trained_weights_meet_north_star_tolerances and, against reference-held vectors, in test_parity_trained.py)."""
     from oracle import spff_oracle as O
     lit = build("SPFF-UNet")
     w = load_det(lit, "SPFF-UNet")
