@@ -60,10 +60,13 @@ int spff_debug_set(int key, long long value);
  * Replaces nn.Conv3d(cin, cout, (3,3,3), padding 1, bias=False) built by `_conv3x3xk`
  * (models.py:616-618) — forward, and the input / weight halves of its convolution_backward.
  * cin, cout multiples of 32 (the Cin = 1 stem has its own entry points below). */
-/* Elements of one packed weight operand: 27*cin*cout bf16. */
+/* Elements (bf16) of one packed weight operand: 2*27*cin*cout — the layouts of the two conv kernels back to back. */
+long long spff_conv3_packed_elems(int cin, int cout);
 /* nn.Conv3d weight [cout][cin][3][3][3] fp32 -> bf16 GEMM operands (either may be NULL):
  *   w_fwd   [cout/32][kh][cin/KC][2-kd][kw][32][KC]        KC = 64 if cin % 64 == 0 else 32
  *   w_dgrad [cin/32][kh][cout/KC'][2-kd][kw][32][KC']      taps flipped, in/out transposed
+ * followed by the halo kernel's [cout/CO][cin/32][kh*3+kw][2-kd][CO][32] (CO = 64 if cout % 64 == 0 else 32; planes whose
+ * height is a multiple of 16 and width a multiple of 8 run that kernel)
  * (opaque to callers: only spff_conv3d_k3_fwd/_fwd_stats/_dgrad consume them). */
 int spff_pack_conv3_weight(const float* w, void* w_fwd, void* w_dgrad, int cout, int cin, void* stream);
 /* y[n,d,h,w,0:cout] = conv3d(x)[...]  (F.conv3d at models.py:616-618 via nn.Sequential :1459-1469) */

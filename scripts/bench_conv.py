@@ -29,6 +29,12 @@ def timeit(fn, iters=5):
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     which = sys.argv[2] if len(sys.argv) > 2 else "fwd,dgrad,wgrad"
+    if len(sys.argv) > 3 and sys.argv[3] == "rows":      # force the flattened-row kernel of conv3_fprop.cu (debug key 7)
+        from spff_b200 import _lib
+        _lib.lib.spff_debug_set(7, 1)
+    if len(sys.argv) > 3 and sys.argv[3].startswith("dbg"):
+        from spff_b200 import _lib
+        _lib.lib.spff_debug_set(5, int(sys.argv[3][3:]))
     for h, cin, cout in LAYERS:
         x = torch.randn(n, 5, h, h, cin, device="cuda").to(torch.bfloat16)
         dy = torch.randn(n, 5, h, h, cout, device="cuda").to(torch.bfloat16)

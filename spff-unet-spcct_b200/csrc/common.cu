@@ -138,6 +138,7 @@ static int g_debug_ctas = 0;
 int debug_ctas() { return g_debug_ctas; }
 static long long g_debug_flags[8] = {0};
 int debug_flag(int key) { return (key >= 0 && key < 8) ? static_cast<int>(g_debug_flags[key]) : 0; }
+long long debug_value(int key) { return (key >= 0 && key < 8) ? g_debug_flags[key] : 0; }
 
 }  // namespace spff
 

@@ -21,6 +21,14 @@ int current_device();
 int debug_ctas();
 // test hook (spff_debug_set key >= 1): generic integer flags, 0 by default. key 1: disable the all-kh wgrad variant
 int debug_flag(int key);
+long long debug_value(int key);   // the same, 64 bit (key 4: device pointer of a cycle-counter buffer, profiling builds of the conv kernels)
+// conv3_halo.cu: the halo-tile formulation of the 3x3x3 convolution (planes tiled by 16 x 8 boxes)
+bool conv3_halo_applicable(spff_shape s, int gemm_k);
+// statistics slots per sample (conv3_fprop.cu; what spff_conv3d_k3_stat_slots reports, whichever kernel runs)
+int conv3_rows_stat_slots(spff_shape s);
+int conv3_halo_pack(const float* w, void* out, int cout, int cin, int dgrad, cudaStream_t st);
+int conv3_halo_launch(const void* x, long long ldx, int cin, const void* wpk, void* y, long long ldy, int cout, spff_shape s,
+                      float* stat_partial, cudaStream_t st);
 // K chunk (channels per TMA box) the conv3 kernels use for a GEMM-K channel count: 64 or 32
 int conv3_kc(int gemm_k_channels);
 

@@ -609,15 +609,25 @@ int spff_pack_conv3_weight(const float* w, void* w_fwd, void* w_dgrad, int cout,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long total = static_cast<long long>(cout) * cin * 27;
   const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  if (w_fwd)
+  // each operand holds two layouts back to back: the flattened-row kernel's, then the halo kernel's (conv3_halo.cu);
+  // which one a launch reads depends on the plane size, unknown here
+  if (w_fwd) {
     spff::pack_conv3_weight_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_fwd), cout, cin,
                                                            spff::conv3_kc(cin), 0);
-  if (w_dgrad)
+    int e = spff::conv3_halo_pack(w, static_cast<__nv_bfloat16*>(w_fwd) + total, cout, cin, 0, st);
+    if (e) return e;
+  }
+  if (w_dgrad) {
     spff::pack_conv3_weight_kernel<<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_dgrad), cout, cin,
                                                            spff::conv3_kc(cout), 1);
+    int e = spff::conv3_halo_pack(w, static_cast<__nv_bfloat16*>(w_dgrad) + total, cout, cin, 1, st);
+    if (e) return e;
+  }
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }
+
+long long spff_conv3_packed_elems(int cin, int cout) { return 2LL * 27 * cin * cout; }
 
 // partial statistics slots per sample of the forward kernel for this shape: qtiles * plane groups
 static int conv3_stat_slots(spff_shape s) {
@@ -641,6 +651,9 @@ static int conv3_common(const void* x, long long ldx, int cin, const void* wpk, 
                    (reinterpret_cast<uintptr_t>(wpk) & 15) == 0,
                "%s: pointers must be 16-byte aligned", who);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (spff::conv3_halo_applicable(s, cin))   // the halo-tile kernel (conv3_halo.cu; second half of the packed operand)
+    return spff::conv3_halo_launch(x, ldx, cin, static_cast<const __nv_bfloat16*>(wpk) + 27LL * cin * cout, y, ldy, cout, s,
+                                   stat_partial, st);
   // cin <= 64: one K chunk per tap, all 27 taps of a 32-channel output block stay resident in smem
   if (stat_partial) {
     if (cin == 64) return spff::launch_fprop<64, true, true>(x, ldx, cin, wpk, y, ldy, cout, s, stat_partial, st);
@@ -683,3 +696,7 @@ int spff_conv3d_k3_dgrad_stats(const void* dy, long long lddy, int cout, const v
 }
 
 }  // extern "C"
+
+namespace spff {
+int conv3_rows_stat_slots(spff_shape s) { return spff_conv3d_k3_stat_slots(s); }
+}  // namespace spff

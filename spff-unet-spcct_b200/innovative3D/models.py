@@ -336,6 +336,23 @@ class UNet3D_SpectralCore(nn.Module):
         if self._engine is not None:
             self._engine.invalidate_weights()
 
+    def stage_ranges(self):
+        """[lo, hi) of the flat buffer per backward stage, in the order their gradients complete: "decoder" (up3 .. out),
+        "bott", "enc3", "enc2", "enc1" (each block with its EFiLM / FourierGate parameters), and "tail" (the SE modules
+        and the lazily registered masks, final only when the whole backward is)."""
+        out = {"decoder": self.decoder_range()}
+        for b in ("enc1", "enc2", "enc3", "bott"):
+            names = [n for n in self._slots if n.split(".")[0] == b and not n.endswith("freq_mask")]
+            lo = min(self._slots[n][0] for n in names)
+            hi = max(self._slots[n][0] + (self._slots[n][1] + 3) // 4 * 4 for n in names)
+            inside = [n for n, (o, k, _) in self._slots.items() if lo <= o < hi]
+            assert sorted(inside) == sorted(names), f"{b} parameters are not contiguous in the flat buffer"
+            out[b] = (lo, hi)
+        out["tail"] = (out["decoder"][1], self._flat_numel)
+        covered = sorted(out.values())
+        assert covered[0][0] == 0 and all(a[1] == b[0] for a, b in zip(covered, covered[1:])) and covered[-1][1] == self._flat_numel
+        return out
+
     def decoder_range(self):
         """[lo, hi) of the flat buffer holding up3 .. out (transposed convs, decoder blocks, head): contiguous
         because parameters are laid out in registration order (enc1..bott, up3, dec3, up2, dec2, up1, dec1, out, se)."""
@@ -532,21 +549,25 @@ class BaseLitModel(pl.LightningModule):
         st["grad"].zero_()
         st["tally"].zero()
         with torch.no_grad():
-            # data parallel: the head/decoder range of the flat gradient buffer is final while the last group's
-            # encoder backward still runs -> its all-reduce is issued there (async, NCCL stream) and overlaps
-            # it; the encoder-side ranges follow at the end. Still ONE bucket layout, two collectives in flight.
-            lo, hi = core.decoder_range()
+            # data parallel: ONE flat gradient buffer, reduced range by range as the last group's backward completes
+            # them (decoder, bottleneck, enc3, enc2, enc1: async on the NCCL stream, overlapping the rest of the
+            # backward); only the small tail (SE modules, lazy masks: ~50 KB) is reduced after the backward.
             pending = []
             hook = None
             if dp.world()[1] > 1:
-                hook = lambda: pending.append(dp.allreduce_async(st["grad"][lo:hi]))
+                if "ranges" not in st:
+                    st["ranges"] = core.stage_ranges()
+                ranges = st["ranges"]
+                hook = lambda stage: pending.append(dp.allreduce_async(st["grad"][ranges[stage][0]:ranges[stage][1]]))
             core.engine.train_step(imgs, lbls, st["G"], st["tally"], group=group, ignore_index=IGNORE_INDEX,
-                                   staged=staged, decoder_done=hook)
+                                   staged=staged, stage_done=hook)
             if pending:
-                gscale = dp.allreduce_grads(st["grad"][:lo])
-                dp.allreduce_grads(st["grad"][hi:])
+                ev = dp.exposed_timer_start()
+                lo, hi = ranges["tail"]
+                gscale = dp.allreduce_grads(st["grad"][lo:hi])
                 for w in pending:
                     w.wait()
+                dp.exposed_timer_stop(ev)
             else:
                 gscale = dp.allreduce_grads(st["grad"])
             if optimize:

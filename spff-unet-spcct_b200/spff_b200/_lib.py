@@ -41,6 +41,7 @@ _LL = c_longlong
 _PROTOTYPES = {
     "spff_device_check": [],
     "spff_debug_set": [c_int, _LL],
+    "spff_conv3_packed_elems": [c_int, c_int],
     "spff_pack_conv3_weight": [_P, _P, _P, c_int, c_int, _P],
     "spff_conv3d_k3_fwd": [_P, _LL, c_int, _P, _P, _LL, c_int, Shape, _P],
     "spff_conv3d_k3_stat_slots": [Shape],
@@ -110,7 +111,7 @@ def _declare():
     for name, argtypes in _PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = c_size_t if name in _SIZE_T_FUNCS else c_int
+        fn.restype = c_size_t if name in _SIZE_T_FUNCS else (c_longlong if name == "spff_conv3_packed_elems" else c_int)
 
 
 _declare()

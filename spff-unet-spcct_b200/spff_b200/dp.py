@@ -53,3 +53,24 @@ def shard_range(total: int, rank: int | None = None, world_size: int | None = No
     base, rem = divmod(total, world_size)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+# Optional measurement of the all-reduce time that is NOT hidden behind the backward: CUDA events on the compute stream
+# around "backward enqueued" -> "every range reduced" (bench.py sets EXPOSED = [] and reads the event pairs).
+EXPOSED = None
+
+
+def exposed_timer_start():
+    if EXPOSED is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def exposed_timer_stop(e0) -> None:
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    EXPOSED.append((e0, e1))

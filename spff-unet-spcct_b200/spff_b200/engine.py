@@ -414,10 +414,12 @@ class SpffEngine:
                 ops.conv3d_k3_dgrad(t1, c, self._packed[f"{b}.1"][1], dxin, cin)
 
     def backward_group(self, B: _GroupBuffers, T: GateTables, G: Dict[str, torch.Tensor],
-                       dlogits: Optional[torch.Tensor], after_decoder: Optional[Callable[[], None]] = None):
+                       dlogits: Optional[torch.Tensor], stage_done: Optional[Callable[[str], None]] = None):
         """Accumulates (+=) every parameter gradient of this group into the fp32 tensors of `G`
         (shaped like the parameters). dlogits: fp32 [n,K,d,h,w], or None when the fused head/loss
-        kernel already left the head's input gradient in B.gout[1] (and its dW/db in G)."""
+        kernel already left the head's input gradient in B.gout[1] (and its dW/db in G).
+        `stage_done(stage)` is called as soon as every gradient of a stage has been enqueued: "decoder" (head, decoder
+        blocks, transposed convs), then "bott", "enc3", "enc2", "enc1" (each with its SE / gate parameters)."""
         p = self.params()
         B.b32.zero()
         if dlogits is not None:
@@ -430,10 +432,12 @@ class SpffEngine:
             xb = B.out[below]
             ops.convt_k122_wgrad(xb, 2 * cu, dy, cu, G[f"{up}.weight"], 1.0)
             ops.convt_k122_dgrad(dy, cu, self._packed[up][1], B.gout[l + 1], 2 * cu)
-        if after_decoder is not None:   # head / decoder / transposed-conv gradients of this group are complete
+        if stage_done is not None:   # head / decoder / transposed-conv gradients of this group are complete
             self._up_bias_grads(B, G)
-            after_decoder()
+            stage_done("decoder")
         self._block_bwd(B, T, G, "bott", B.gout[4], B.pool[3], B.dpool[3])
+        if stage_done is not None:
+            stage_done("bott")
         for l, enc in ((3, "enc3"), (2, "enc2"), (1, "enc1")):
             c = B.C[l]
             dskip = B.dcat[l][..., c:]
@@ -442,7 +446,9 @@ class SpffEngine:
                 self._block_bwd(B, T, G, enc, dskip, B.pool[l - 1], B.dpool[l - 1])
             else:
                 self._block_bwd(B, T, G, enc, dskip, None, None)
-        if after_decoder is None:
+            if stage_done is not None:
+                stage_done(enc)
+        if stage_done is None:
             self._up_bias_grads(B, G)
 
     @staticmethod
@@ -581,15 +587,15 @@ class SpffEngine:
 
     def train_step(self, x: torch.Tensor, labels: torch.Tensor, G: Dict[str, torch.Tensor], tally: "LossTally",
                    group: int = 32, ignore_index: int = 255, staged: Optional["StagedBatch"] = None,
-                   decoder_done: Optional[Callable[[], None]] = None):
+                   stage_done: Optional[Callable[[str], None]] = None):
         """Fused forward + CE/confusion + backward over the batch in sample groups. Accumulates the
         parameter gradients of the batch-mean CE (helpers.py:798-801; the Dice term of the loss has
         no gradient, helpers.py:782-795) into G and the loss statistics into `tally`.
         `staged`: the batch is still arriving from pinned host memory on a copy stream (StagedBatch);
         each group's forward waits only for its own slice.
-        `decoder_done`: called once, inside the LAST group's backward, as soon as every gradient of the
-        head, the decoder blocks and the transposed convs is final (data-parallel: their all-reduce
-        then overlaps the encoder's backward)."""
+        `stage_done(stage)`: called inside the LAST group's backward as soon as every gradient of a stage is final —
+        "decoder" (head, decoder blocks, transposed convs), "bott", "enc3", "enc2", "enc1" — so that a data-parallel
+        caller can start that range's all-reduce while the rest of the backward still runs."""
         x = self._check_input(x)
         bsz, _, d, h, w = x.shape
         if labels.shape != (bsz, d, h, w):
@@ -615,11 +621,11 @@ class SpffEngine:
                                 G["out.weight"].view(-1, self.cfg.base), G["out.bias"], 1.0)
             last = hi == bsz
             hook = None
-            if last and decoder_done is not None:
-                def hook():
-                    T.finish(G, ("dec3", "dec2", "dec1"))
-                    decoder_done()
-            self.backward_group(B, T, G, None, after_decoder=hook)
+            if last and stage_done is not None:
+                def hook(stage):
+                    T.finish(G, ("dec3", "dec2", "dec1") if stage == "decoder" else (stage,))
+                    stage_done(stage)
+            self.backward_group(B, T, G, None, stage_done=hook)
         T.finish(G)
 
 

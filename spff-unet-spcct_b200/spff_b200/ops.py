@@ -39,8 +39,9 @@ def pack_conv3_weight(w: torch.Tensor, fwd: bool = True, dgrad: bool = True):
     """nn.Conv3d weight [Cout,Cin,3,3,3] fp32 -> (w_fwd, w_dgrad) bf16 GEMM operands."""
     cout, cin = w.shape[0], w.shape[1]
     w = w.detach().contiguous().float()
-    wf = torch.empty(27 * cin * cout, dtype=torch.bfloat16, device=w.device) if fwd else None
-    wd = torch.empty(27 * cin * cout, dtype=torch.bfloat16, device=w.device) if dgrad else None
+    elems = int(_lib.lib.spff_conv3_packed_elems(cin, cout))
+    wf = torch.empty(elems, dtype=torch.bfloat16, device=w.device) if fwd else None
+    wd = torch.empty(elems, dtype=torch.bfloat16, device=w.device) if dgrad else None
     call("spff_pack_conv3_weight", ptr(w), ptr(wf), ptr(wd), cout, cin, stream_ptr())
     return wf, wd
 

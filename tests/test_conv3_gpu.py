@@ -26,6 +26,17 @@ def _from_ndhwc(buf, c):
     return buf[..., :c].permute(0, 4, 1, 2, 3).float()
 
 
+@pytest.fixture(params=["auto", "rows", "halo"])
+def conv_kernel(request):
+    """Two kernels implement forward / dgrad (flattened-row: conv3_fprop.cu, halo-tile: conv3_halo.cu; the library picks one
+    per shape and channel count). Every case runs under the default choice and with either kernel forced (debug key 7;
+    a forced halo kernel still needs planes that tile by 16 x 8 and falls back otherwise)."""
+    from spff_b200 import _lib
+    _lib.lib.spff_debug_set(7, {"auto": 0, "rows": 1, "halo": 2}[request.param])
+    yield request.param
+    _lib.lib.spff_debug_set(7, 0)
+
+
 CASES = [
     # n, d, h, w, cin, cout
     (2, 5, 16, 16, 32, 32),
@@ -46,11 +57,16 @@ CASES = [
     (2, 5, 128, 128, 64, 32),
     (2, 5, 64, 64, 128, 64),
     (5, 5, 32, 32, 128, 128),
+    # depth 16 (SP_UNet / 3DUNet: four plane groups of four) and depth 7 (ragged groups) on planes the halo kernel tiles
+    (1, 16, 16, 16, 32, 32),
+    (1, 16, 16, 8, 64, 64),
+    (2, 7, 32, 16, 128, 64),
+    (1, 3, 16, 16, 256, 128),
 ]
 
 
 @pytest.mark.parametrize("n,d,h,w,cin,cout", CASES)
-def test_conv3_fwd(n, d, h, w, cin, cout):
+def test_conv3_fwd(n, d, h, w, cin, cout, conv_kernel):
     from spff_b200 import ops
 
     torch.backends.cudnn.allow_tf32 = False
@@ -70,7 +86,7 @@ def test_conv3_fwd(n, d, h, w, cin, cout):
 
 
 @pytest.mark.parametrize("n,d,h,w,cin,cout", CASES[:7] + CASES[10:])
-def test_conv3_dgrad(n, d, h, w, cin, cout):
+def test_conv3_dgrad(n, d, h, w, cin, cout, conv_kernel):
     from spff_b200 import ops
 
     torch.backends.cudnn.allow_tf32 = False
@@ -153,7 +169,7 @@ def test_conv3_wgrad(n, d, h, w, cin, cout):
 
 
 @pytest.mark.parametrize("n,d,h,w,cin,cout", CASES)
-def test_conv3_fwd_with_fused_statistics(n, d, h, w, cin, cout):
+def test_conv3_fwd_with_fused_statistics(n, d, h, w, cin, cout, conv_kernel):
     """spff_conv3d_k3_fwd_stats: same output as the plain forward (bit-exact) and InstanceNorm
     coefficients from its per-item partial statistics == those of the separate statistics pass
     (mean to 1e-4 abs of a unit-scale tensor, rstd to 1e-3 rel: the fused statistics see the fp32
