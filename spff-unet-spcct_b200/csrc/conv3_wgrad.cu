@@ -167,13 +167,18 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_con
       const uint64_t adesc_hi = make_smem_desc_hi(kSlotBytes, kSboA, kSwzA);
       const uint64_t bdesc_hi = make_smem_desc_hi(C::XT, kSboB, kSwzB);
       const uint32_t idesc = make_idesc_bf16(128, C::N, 1, 1);
+      // COB = 64: the second MMA of an x plane covers the dy planes d'+1 and d'+2, and only d'+1 is a tap (kd = 0). It
+      // is issued with M = 64 - same tensor time, but a third less of the A operand crosses shared memory, which is
+      // what bounds these MMAs - and not at all when d'+1 lies outside the volume (zero padding). An M = 64 accumulator
+      // keeps row r in TMEM lane (r % 16) + 32 * (r / 16) (scripts/micro/umma_m64.cu); the reduction kernel reads it so.
+      const uint32_t idesc_half = make_idesc_bf16(64, C::N, 1, 1);
       const int ksteps = rows / 16;
       // descriptors advance by additions on the (address >> 4) field (the smem window is < 256 KB)
       const uint64_t adesc0 = smem_desc(adesc_hi, smem_u32(sDy));
       const uint64_t bdesc0 = smem_desc(bdesc_hi, smem_u32(sX));
       int xs = 0, ds = 0;
       uint32_t xph = 0, dph = 0;
-      uint32_t first = 1;
+      uint32_t first = 1, first1 = 1;    // accumulator 0 / accumulator 1 not written yet
       for (long long t = t_begin; t < t_end; ++t) {
         for (int pg = 0; pg < p.ngroups; ++pg) {
           const int d0 = pg * p.G;
@@ -189,11 +194,16 @@ conv3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_con
             for (int i = 0; i < C::NMMA; ++i) {
               uint64_t ad = dydesc + static_cast<uint64_t>((dp - d0 + i * C::SP) * (kSlotBytes >> 4));
               uint64_t bd = xdesc;
+              const bool half = (C::SP == 2) && (i == 1);
+              if (half && dp + 1 >= p.d && !first1) continue;     // the only tap of this MMA reads zero padding
+              const uint32_t id = half ? idesc_half : idesc;
+              const uint32_t fresh = half ? first1 : first;
               for (int ks = 0; ks < ksteps; ++ks) {
-                if (leader) umma_bf16(tmem_base + i * C::N, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+                if (leader) umma_bf16(tmem_base + i * C::N, ad, bd, id, (fresh && ks == 0) ? 0u : 1u);
                 ad += (2 * kSboA) >> 4;
                 bd += (2 * kSboB) >> 4;
               }
+              if (half) first1 = 0;
             }
             first = 0;
             if (leader) umma_commit(&xempty[xs]);
@@ -260,7 +270,8 @@ __global__ void conv3_wgrad_reduce_kernel(const float* __restrict__ partial, flo
     const int item = (kh * ncob + cob) * ncib + cib;
     const int o = 2 - kd;  // plane offset index: i*SP + b
     const int i = o / SP, b = o % SP;
-    const int lane = b * COB + col;
+    // COB = 64: accumulator 1 is written by M = 64 MMAs, whose row r lives in TMEM lane (r % 16) + 32 * (r / 16)
+    const int lane = (SP == 2 && i == 1) ? (col % 16) + 32 * (col / 16) : b * COB + col;
     const int column = kw * CIB + cic;
     float acc = 0.f;
     for (int s = 0; s < ksplit; ++s)
