@@ -52,53 +52,131 @@ def load_peaks():
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores
+# CPU arm: the reference itself (staged copy under baseline/_ref), else the oracle port, on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_step_time(samples: int, reps: int, warmup: int, budget_s: float = 1e9):
-    """Times `reps` steps (fwd + loss + bwd, CPU fp32, all host threads) of the oracle port on
-    `samples` slices of the bench shape; returns (seconds per step list, threads)."""
-    import torch
+REF_STAGED = os.path.join(ROOT, "baseline", "_ref")
+REF_SLICES_MAX = 32      # 32 slices [1,5,128,128] = 2 621 440 voxels = the voxel count of BASELINE configs[0] (12 GB RSS)
 
-    from oracle import spff_oracle as O
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    torch.manual_seed(42)
-    p = O.det_weights(O.param_shapes("SPFF-UNet"), seed=42)
+
+def _cpu_inputs(samples: int):
+    import torch
     g = torch.Generator().manual_seed(42)
     x = torch.randn(samples, 1, FRAMES, H, W, generator=g)
     lab = torch.randint(0, NUM_CLASSES, (samples, FRAMES, H, W), generator=g)
+    return x, lab
+
+
+def _reference_stepper():
+    """(step(x, lab), kind): fwd + ce_plus_macro_dice_loss + backward of SPFF-UNet on the CPU in fp32.
+    kind "reference": the UNMODIFIED reference modules (`config.VARIANTS["SPFF-UNet"]` of baseline/_ref, the git-ignored
+    copy of /root/reference that __graft_entry__.build() stages and gpurun ships), imported under inert stubs for the
+    plotting / Lightning packages this image lacks - none of this repo's package is on that path. kind "port": the
+    oracle restatement (oracle/spff_oracle.py, pinned to the reference by tests/golden) when no staged copy exists."""
+    import torch
+    if os.path.isfile(os.path.join(REF_STAGED, "innovative3D", "models.py")):
+        pkg = os.path.join(ROOT, "spff-unet-spcct_b200")
+        sys.path[:] = [p for p in sys.path if os.path.abspath(p) != pkg]      # this repo's `innovative3D` must not shadow it
+        for k in [k for k in sys.modules if k == "innovative3D" or k.startswith("innovative3D.")]:
+            del sys.modules[k]
+        from oracle.make_golden import install_stubs
+        install_stubs()
+        os.environ.setdefault("CHECKPOINT_DIR", os.path.join(tempfile.gettempdir(), "spff_ref_ckpt"))
+        os.environ.setdefault("LOG_DIR", os.path.join(tempfile.gettempdir(), "spff_ref_logs"))
+        from pathlib import Path
+        _mkdir = Path.mkdir
+
+        def safe_mkdir(self, *a, **k):      # config.py:15-19 creates directories under a hard-coded home path
+            try:
+                return _mkdir(self, *a, **k)
+            except OSError:
+                return None
+
+        Path.mkdir = safe_mkdir
+        sys.path.insert(0, REF_STAGED)
+        try:
+            import innovative3D.config as RC
+        finally:
+            Path.mkdir = _mkdir
+        assert os.path.abspath(RC.__file__).startswith(REF_STAGED), RC.__file__
+        torch.manual_seed(42)
+        lit = dict((v[0], v[1]) for v in RC.VARIANTS)["SPFF-UNet"]()
+        lit.train()
+
+        def step(x, lab):
+            lit.zero_grad(set_to_none=True)
+            loss = lit.compute_loss(lit(x), lab)
+            loss.backward()
+            return float(loss)
+        return step, "reference"
+    from oracle import spff_oracle as O
+    torch.manual_seed(42)
+    p = O.det_weights(O.param_shapes("SPFF-UNet"), seed=42)
+    return (lambda x, lab: O.loss_and_grads(p, x, lab, "SPFF-UNet")[0]), "port"
+
+
+def cpu_step_time(samples: int, reps: int, warmup: int, budget_s: float = 1e9):
+    """Times `reps` steps (fwd + loss + bwd, CPU fp32, all host threads) on `samples` slices of the bench shape;
+    returns (seconds per step list, threads, kind)."""
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    step, kind = _reference_stepper()
+    x, lab = _cpu_inputs(samples)
     times = []
     t_start = time.perf_counter()
     for i in range(warmup + reps):
         t0 = time.perf_counter()
-        O.loss_and_grads(p, x, lab, "SPFF-UNet")
+        step(x, lab)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
         if time.perf_counter() - t_start > budget_s and times:
             break
-    return times, threads
+    return times, threads, kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (its torch CPU fp32
-    operator sequence, restated in oracle/spff_oracle.py and pinned to the reference by
-    tests/golden) on the host cores. Rank 0 only; a step is a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, all threads. Rank 0 only; a
+    step is a bounded sample of the workload: as many slices (8..32) as keep the whole --steps/--warmup run under ~4
+    minutes, found with one calibration step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    samples = 4
-    times, threads = cpu_step_time(samples, args.steps, args.warmup)
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    step, kind = _reference_stepper()
+    x8, l8 = _cpu_inputs(8)
+    step(x8[:2], l8[:2])                               # first-call set-up (lazy parameters, oneDNN primitives)
+    t0 = time.perf_counter()
+    step(x8, l8)
+    per_slice = (time.perf_counter() - t0) / 8
+    n_steps = args.steps + args.warmup
+    samples = REF_SLICES_MAX
+    while samples > 8 and per_slice * samples * n_steps > 240.0:
+        samples //= 2
+    samples = int(os.environ.get("SPFF_REF_SLICES", samples))
+    x, lab = _cpu_inputs(samples)
+    times = []
+    for i in range(n_steps):
+        t0 = time.perf_counter()
+        step(x, lab)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
     vox = samples * FRAMES * H * W
     sec = sum(times) / len(times)
     value = vox / sec
-    sample = f"{samples} of the {SAMPLES} slices [1,5,{H},{W}] per step, fp32, fwd+loss+bwd, {threads} threads"
+    sample = (f"{samples} of the {SAMPLES} slices [1,5,{H},{W}] per step ({vox} voxels), fp32 fwd+loss+bwd, {threads} threads, "
+              f"{'the reference modules themselves (baseline/_ref)' if kind == 'reference' else 'oracle port'}")
+    cfg = workload_config(args.gpus)
+    cfg["workload"] += f" - CPU arm: a bounded sample of {samples} slices per step"
+    cfg["samples_per_step_timed"] = samples
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -228,7 +306,9 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    per_rank = {}
+
+    def timed(fn, steps, tag=None):
         barrier()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -239,6 +319,10 @@ def run_b200(args):
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
+            if tag is not None:      # every rank's own time: which rank is the slow one, and by how much
+                allt = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(allt, t)
+                per_rank[tag] = [float(v) / steps for v in allt]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t) * 1e-3
 
@@ -260,14 +344,25 @@ def run_b200(args):
     prof = _lib.Profile(select=lambda n: n in conv_names)
     calls0 = _lib.CALLS
     _lib.PROFILE = prof
-    sec = timed(step_resident, args.steps)
+    from spff_b200 import dp as _dp
+    _dp.EXPOSED = [] if world > 1 else None
+    sec = timed(step_resident, args.steps, tag="ms_per_step")
+    exposed_ms = None
+    if world > 1:      # all-reduce time NOT hidden behind the backward (compute stream: backward enqueued -> every range reduced)
+        torch.cuda.synchronize()
+        mine = sum(a.elapsed_time(b) for a, b in _dp.EXPOSED) / max(1, len(_dp.EXPOSED))
+        t = torch.tensor([mine], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        exposed_ms = [float(v) for v in allt]
+        _dp.EXPOSED = None
     _lib.PROFILE = None
     launches = _lib.CALLS - calls0
     clk = clocks.stop()
     conv = prof.summary()
     # ---- end-to-end steps from pinned host memory ----
     step_e2e()
-    sec_e2e = timed(step_e2e, args.steps)
+    sec_e2e = timed(step_e2e, args.steps, tag="e2e_ms_per_step")
     # ---- one extra step with every call timed: breakdown by entry point ----
     full = _lib.Profile()
     _lib.PROFILE = full
@@ -313,19 +408,56 @@ def run_b200(args):
             "breakdown_total_ms": round(total_ms, 3),
             "final_loss": final_loss,
         }
-        if not args.no_cpu and world >= 1 and variant == "SPFF-UNet":
-            t0 = time.perf_counter()
-            cs = 8
-            times, threads = cpu_step_time(cs, reps=4, warmup=1, budget_s=25.0)
-            cpu_sec = min(times)
-            line["cpu_baseline"] = {
-                "value": cs * FRAMES * H * W / cpu_sec, "unit": "voxels/s", "cores": threads, "kind": "port",
-                "sample": f"{cs} of the {samples} slices [1,5,{H},{W}] per step, fp32 fwd+loss+bwd, best of {len(times)} "
-                          f"({time.perf_counter() - t0:.0f} s of CPU work)"}
+        if world > 1:
+            line["per_rank"] = {**per_rank, "allreduce_exposed_ms": exposed_ms,
+                                "note": "per-rank device time per step (the line's ms_per_step is their max) and the part of the "
+                                        "gradient all-reduce that is not hidden behind the backward"}
+        if not args.no_extras and world == 1 and variant == "SPFF-UNet":
+            # BASELINE.json configs[3] (the controls) and configs[4] (inference scan), measured in this same process so that
+            # the driver's record holds them; each is the full line `--variant X` / `--mode infer` prints, fewer steps
+            del x_dev, lab_dev
+            lit.model.engine.release_buffers()
+            torch.cuda.empty_cache()
+            line["extra"] = run_extras(args)
+        if not args.no_cpu and world == 1 and variant == "SPFF-UNet":
+            # the reference's CPU path on this box's host cores: a separate process (this one holds this repo's
+            # `innovative3D`; the reference's package of the same name cannot be imported beside it)
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "0"],
+                                     capture_output=True, text=True, timeout=600, env={**os.environ, "SPFF_REF_SLICES": "8"})
+                ref = json.loads(out.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = ref["cpu_baseline"]
+            except Exception as e:      # the GPU numbers stand on their own
+                line["cpu_baseline"] = {"value": None, "unit": "voxels/s", "cores": os.cpu_count(), "kind": "unavailable",
+                                        "sample": f"reference leg failed: {e!r}"[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_extras(args):
+    """PlainCore_UNet / 3DUNet training steps and the inference scan, as sub-lines of the default run."""
+    import copy
+    import io
+    from contextlib import redirect_stdout
+    out = {}
+    for key, mode, variant in (("plaincore", "train", "PlainCore_UNet"), ("unet3d", "train", "3DUNet"), ("infer", "infer", "SPFF-UNet")):
+        a = copy.copy(args)
+        a.variant, a.mode, a.no_cpu, a.no_extras = variant, mode, True, True
+        a.steps, a.warmup = min(args.steps, 3), 3
+        buf = io.StringIO()
+        try:
+            with redirect_stdout(buf):
+                (run_infer if mode == "infer" else run_b200)(a)
+            d = json.loads(buf.getvalue().strip().splitlines()[-1])
+            out[key] = {k: d[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "config", "e2e", "roofline", "gpu_launches")
+                        if k in d}
+        except Exception as e:
+            out[key] = {"error": repr(e)[:300]}
+        import torch
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_infer(args):
@@ -423,6 +555,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[3] / configs[4] sub-lines of the default run")
     ap.add_argument("--variant", default="SPFF-UNet",
                     choices=["SPFF-UNet", "E_SP_UNet", "FG_SP_UNet", "SP_UNet", "PlainCore_UNet", "3DUNet"],
                     help="SPFF-UNet is the headline (BASELINE.json configs[1]); the others are the controls of configs[3]")
