@@ -207,9 +207,9 @@ def conv_traffic():
     (profiles/r01f_conv_traffic.json: every conv launch of `SPFF_BENCH_SAMPLES=256 bench.py`, i.e. the same 256-slice
     launches as the default sample group). None when the capture is absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01f_conv_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_conv_traffic.json")) as f:
             k = json.load(f)["kernels"]
-        rows = [v for name, v in k.items() if "conv3_fprop_kernel" in name]
+        rows = [v for name, v in k.items() if "conv3_fprop_kernel" in name or "conv3_halo_kernel" in name]
         n = sum(v["launches"] for v in rows)
         return sum(v["launches"] * (v["dram_read_bytes_per_launch"] + v["dram_write_bytes_per_launch"]) for v in rows) / n
     except Exception:

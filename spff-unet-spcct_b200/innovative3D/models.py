@@ -203,6 +203,9 @@ class _CoreFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         core = ctx.core
+        if ctx.state is None:
+            raise RuntimeError("UNet3D_SpectralCore (B200 build): the activations of this forward were released by its "
+                               "first backward; retain_graph / a second backward through the same forward is not supported")
         flat = torch.zeros(core._flat_numel, device=dlogits.device)
         G = core._views(flat)
         core.engine.backward_saved(ctx.state, dlogits, G)
@@ -784,13 +787,21 @@ class _CicekFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, net, target_depth, *params):
-        logits, state = net.engine.forward_saved(x, target_depth, training=net.training)
+        if not net.training:
+            # the backward kernels implement training-mode BatchNorm (batch statistics: mean / projection terms in dx);
+            # eval-mode BatchNorm has a different input gradient, so gradients in eval() would be silently wrong
+            raise NotImplementedError("Cicek3DUNet (B200 build): gradients through eval-mode BatchNorm (running statistics) "
+                                      "are not implemented; call .train(), or run the forward under torch.no_grad()")
+        logits, state = net.engine.forward_saved(x, target_depth, training=True)
         ctx.net, ctx.state = net, state
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         net = ctx.net
+        if ctx.state is None:
+            raise RuntimeError("Cicek3DUNet (B200 build): the activations of this forward were released by its first "
+                               "backward; retain_graph / a second backward through the same forward is not supported")
         flat = torch.zeros(net._flat_numel, device=dlogits.device)
         G = net._views(flat)
         net.engine.backward_saved(ctx.state, dlogits, G)

@@ -414,3 +414,27 @@ def test_errors():
         L(num_classes=13, class_weights=[1.0] * 13)
     with pytest.raises(NotImplementedError):
         L(num_classes=13, dice_weight=0.5)
+
+
+
+def test_eval_mode_gradients_and_second_backward_are_loud():
+    """The backward kernels implement training-mode BatchNorm: asking for gradients in eval() raises instead of
+    returning the training-mode gradient; a second backward through one forward raises a clear error."""
+    from innovative3D import config as C
+    lit = dict((v[0], v[1]) for v in C.VARIANTS)["3DUNet"]().cuda()
+    x = torch.randn(2, 1, 5, 16, 16, device="cuda")
+    lit.eval()
+    with pytest.raises(NotImplementedError, match="eval-mode BatchNorm"):
+        lit(x)
+    with torch.no_grad():
+        assert lit(x).shape == (2, 13, 5, 16, 16)          # inference in eval mode is fine
+    lit.train()
+    out = lit(x)
+    out.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second backward"):
+        out.sum().backward()
+    spff = dict((v[0], v[1]) for v in C.VARIANTS)["SPFF-UNet"]().cuda()
+    o2 = spff(x)
+    o2.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second backward"):
+        o2.sum().backward()

@@ -208,3 +208,42 @@ def test_conv3_fwd_with_fused_statistics(n, d, h, w, cin, cout, conv_kernel):
     ref = F.conv3d(_from_ndhwc(x, cin).double(), wt.to(torch.bfloat16).double(), padding=1)
     assert torch.allclose(coef_p[..., 2].double(), ref.mean(dim=(2, 3, 4)), atol=1e-5)
     assert torch.allclose(coef_p[..., 3].double(), 1.0 / torch.sqrt(ref.var(dim=(2, 3, 4), unbiased=False) + 1e-5), rtol=1e-4)
+
+
+
+@pytest.mark.parametrize("noise,bound", [(0.09, 5e-4), (0.009, 1e-2)])
+def test_fused_statistics_when_the_mean_dwarfs_sigma(noise, bound, conv_kernel):
+    """InstanceNorm statistics from the conv epilogue when |mean| >> sigma: an almost constant positive input through
+    all-positive centre-tap weights (no zero-padding effect at the borders) gives an output whose mean is ~50 sigma
+    (noise 0.09) or ~500 sigma (noise 0.009). The variance comes
+    from fp32 per-tile {sum, sum of squares} partials combined in double (E[x^2] - mean^2): the cancellation costs
+    ~mean^2 / sigma^2 * 2^-24 per tile, measured rstd error 1e-4 at 50 sigma and 0.4 % at 500 sigma (asserted: 5e-4 / 1e-2).
+    A network input with mean / sigma beyond a few hundred per (sample, channel) - never the case after the first
+    InstanceNorm of the graph - would need shifted partials."""
+    from spff_b200 import ops
+    from spff_b200._lib import Shape
+
+    n, d, h, w, cin, cout = 2, 5, 32, 32, 32, 32
+    g = torch.Generator().manual_seed(21)
+    x = (1.0 + noise * torch.randn(n, cin, d, h, w, generator=g)).cuda()
+    wt = torch.zeros(cout, cin, 3, 3, 3)
+    wt[:, :, 1, 1, 1] = torch.randn(cout, cin, generator=g).abs() * (1.0 / cin)
+    wt = wt.cuda()
+    xb = _to_ndhwc_bf16(x)
+    wf, _ = ops.pack_conv3_weight(wt)
+    y = torch.empty(n, d, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    slots = ops.conv3d_k3_stat_slots(Shape(n, d, h, w))
+    partial = torch.empty(n, slots, 2, cout, device="cuda")
+    ops.conv3d_k3_fwd_stats(xb, cin, wf, y, cout, partial)
+    coef = torch.empty(n, cout, 4, device="cuda")
+    ops.in_coeffs_from_partials(partial, slots, torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda"), 1e-5, n, cout,
+                                d * h * w, coef)
+    ref = F.conv3d(_from_ndhwc(xb, cin).double(), wt.to(torch.bfloat16).double(), padding=1)
+    mean, var = ref.mean(dim=(2, 3, 4)), ref.var(dim=(2, 3, 4), unbiased=False)
+    ratio = float((mean.abs() / var.sqrt()).median())
+    assert ratio > (30 if noise > 0.05 else 300), ratio
+    rstd_ref = 1.0 / torch.sqrt(var + 1e-5)
+    err = float(((coef[..., 3].double() - rstd_ref).abs() / rstd_ref).max())
+    print(f"mean/sigma {ratio:.0f}: worst relative rstd error {err:.2e}")
+    assert torch.allclose(coef[..., 2].double(), mean, rtol=1e-6)
+    assert err < bound, err
