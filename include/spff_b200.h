@@ -152,6 +152,15 @@ int spff_norm_act_reduce(const void* x, long long ldx, const float* coef, float*
 int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, const float* P, const float* Q,
                                void* y, long long ldy, void* ypool, long long ldp, int c, spff_shape s, float slope,
                                void* stream);
+/* Parameter-only tables of the gates and their backward (EnergyFiLM3D models.py:1494-1512: g1 = 1 + tanh(gamma), bt = beta,
+ * each [c][frames], from the MLP weights w0 [32][16], b0 [32], w2 [2c][32], b2 [2c] over the sinusoidal bin code;
+ * FourierGate3D models.py:1537-1542: kfg [frames] = irfft(freq_mask [frames/2+1] * mag_scale [1])). A NULL w0 / freq_mask
+ * skips that gate. The backward ACCUMULATES (+=) the parameter gradients from dg1 / dbt / dkfg. frames <= 16. */
+int spff_gate_tables_fwd(const float* w0, const float* b0, const float* w2, const float* b2, const float* freq_mask,
+                         const float* mag_scale, int c, int frames, float* g1, float* bt, float* kfg, void* stream);
+int spff_gate_tables_bwd(const float* w0, const float* b0, const float* w2, const float* b2, const float* freq_mask,
+                         const float* mag_scale, int c, int frames, const float* dg1, const float* dbt, const float* dkfg,
+                         float* dw0, float* db0, float* dw2, float* db2, float* dfreq_mask, float* dmag_scale, void* stream);
 /* Gate micro-kernel: S[n][d][c] -> P,Q[n][d][c]. Tables (fp32, device): g1[c][d] = 1 + tanh(gamma),
  * bt[c][d] = beta of EnergyFiLM (input independent, models.py:1494-1512); kfg[d]: the circular
  * kernel irfft(freq_mask*mag_scale) of FourierGate (models.py:1537-1542); se_w1[hid][c], se_b1[hid],
@@ -266,6 +275,17 @@ int spff_maxpool222_bwd_add(const void* dpool, long long ldp, const void* y, lon
 int spff_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, float lr, float momentum,
                   float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
 
+/* ---- per-step scalars of the fused training step (no framework launches inside fit_step) ----------------------
+ * Number of labels != ignore_index (the CE normaliser N_valid of F.cross_entropy, helpers.py:798); labels uint8 or int64. */
+int spff_count_valid(const void* labels, int label_bytes, long long total, int ignore_index, unsigned long long* out,
+                     void* stream);
+/* ce_plus_macro_dice_loss (helpers.py:782-803) from the tally spff_head_loss_fused / spff_ce_confusion accumulate:
+ * out = nll / max(count, 1) + 0.5 * (1 - mean_{c=1..k-1} (2tp+s)/(2tp+fp+fn+s)), confusion [label][argmax]. */
+int spff_loss_from_tally(const double* nll, const unsigned long long* count, const unsigned long long* confusion, int k,
+                         double smooth, float* out, void* stream);
+/* out[c] += sum_r m[r * row_stride + c] for c < cols (double accumulation, fixed order): the bias gradient of a
+ * ConvTranspose3d from the column sums spff_conv3d_k3_dgrad_stats left per work item (models.py:668-672). */
+int spff_partial_colsum(const float* m, long long rows, long long row_stride, int cols, float* out, void* stream);
 /* ---- optimizer (models.py:591-594: torch.optim.Adam, lr 1e-4, betas (0.9,0.999), eps 1e-8) -------- */
 int spff_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float grad_scale, void* stream);

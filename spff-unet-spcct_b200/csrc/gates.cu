@@ -427,6 +427,143 @@ int check_gate_args(const GateArgs& a, int n) {
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Parameter-only tables of the gates, and their backward (one CTA per block; replaces ~40 tiny tensor ops + an
+// autograd pass per block and step):
+//   EnergyFiLM3D (models.py:1494-1512): pe[j][f] sinusoidal code of the bin index (16 rows), h = relu(W0 pe + b0) [32][F],
+//     gb = W2 h + b2 [2C][F], g1 = 1 + tanh(gb[:C]), bt = gb[C:]
+//   FourierGate3D (models.py:1537-1542): kfg = irfft(freq_mask * mag_scale, n = F)  (real spectrum of L = F/2 + 1 bins)
+// ---------------------------------------------------------------------------------------------
+constexpr int kPe = 16, kHidE = 32, kMaxF = 16;
+
+__device__ __forceinline__ float pe_value(int j, int f) {
+  const int half = kPe / 2;
+  const int i = j < half ? j : j - half;
+  const float denom = expf(static_cast<float>(i) * (-logf(10000.f) / static_cast<float>(half)));
+  const float a = static_cast<float>(f) * denom;
+  return j < half ? sinf(a) : cosf(a);
+}
+// weight of spectral bin l in the inverse real FFT of length F: x[t] = (1/F) sum_l w_l M_l cos(2 pi l t / F)
+__device__ __forceinline__ float irfft_weight(int l, int F) { return (l == 0 || (F % 2 == 0 && l == F / 2)) ? 1.f : 2.f; }
+
+__global__ void gate_tables_fwd_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2,
+                                       const float* __restrict__ b2, const float* __restrict__ mask,
+                                       const float* __restrict__ scale, int C, int F, float* __restrict__ g1,
+                                       float* __restrict__ bt, float* __restrict__ kfg) {
+  __shared__ float pe[kPe][kMaxF];
+  __shared__ float h[kHidE][kMaxF];
+  const int tid = threadIdx.x;
+  if (w0) {
+    for (int i = tid; i < kPe * F; i += blockDim.x) pe[i / F][i % F] = pe_value(i / F, i % F);
+    __syncthreads();
+    for (int i = tid; i < kHidE * F; i += blockDim.x) {
+      const int k = i / F, f = i % F;
+      float a = b0[k];
+      for (int j = 0; j < kPe; ++j) a = fmaf(w0[k * kPe + j], pe[j][f], a);
+      h[k][f] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * C * F; i += blockDim.x) {
+      const int m = i / F, f = i % F;
+      float a = b2[m];
+      for (int k = 0; k < kHidE; ++k) a = fmaf(w2[m * kHidE + k], h[k][f], a);
+      if (m < C) g1[m * F + f] = 1.f + tanhf(a);
+      else bt[(m - C) * F + f] = a;
+    }
+  }
+  if (mask && tid < F) {
+    const int L = F / 2 + 1;
+    const float sc = scale[0];
+    float a = 0.f;
+    for (int l = 0; l < L; ++l)
+      a += irfft_weight(l, F) * mask[l] * sc * cospif(2.f * static_cast<float>((l * tid) % F) / static_cast<float>(F));
+    kfg[tid] = a / static_cast<float>(F);
+  }
+}
+
+// Accumulates (+=) the parameter gradients from the table gradients dg1 / dbt [C][F] and dkfg [F]. One CTA; every
+// output element has one writer, sums run in a fixed order.
+__global__ void gate_tables_bwd_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2,
+                                       const float* __restrict__ b2, const float* __restrict__ mask,
+                                       const float* __restrict__ scale, int C, int F, const float* __restrict__ dg1,
+                                       const float* __restrict__ dbt, const float* __restrict__ dkfg, float* __restrict__ dw0,
+                                       float* __restrict__ db0, float* __restrict__ dw2, float* __restrict__ db2,
+                                       float* __restrict__ dmask, float* __restrict__ dscale) {
+  extern __shared__ float sm[];
+  const int tid = threadIdx.x;
+  if (w0) {
+    float* pe = sm;                      // [kPe][F]
+    float* pre = pe + kPe * F;           // [kHidE][F]  pre-activation of the hidden layer
+    float* dgb = pre + kHidE * F;        // [2C][F]
+    float* dh = dgb + 2 * C * F;         // [kHidE][F]
+    for (int i = tid; i < kPe * F; i += blockDim.x) pe[i] = pe_value(i / F, i % F);
+    __syncthreads();
+    for (int i = tid; i < kHidE * F; i += blockDim.x) {
+      const int k = i / F, f = i % F;
+      float a = b0[k];
+      for (int j = 0; j < kPe; ++j) a = fmaf(w0[k * kPe + j], pe[j * F + f], a);
+      pre[i] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * C * F; i += blockDim.x) {
+      const int m = i / F, f = i % F;
+      if (m < C) {
+        float a = b2[m];
+        for (int k = 0; k < kHidE; ++k) a = fmaf(w2[m * kHidE + k], fmaxf(pre[k * F + f], 0.f), a);
+        const float th = tanhf(a);
+        dgb[i] = dg1[m * F + f] * (1.f - th * th);
+      } else {
+        dgb[i] = dbt[(m - C) * F + f];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * C * (kHidE + 1); i += blockDim.x) {     // dW2 [2C][32] and db2 [2C]
+      const int m = i / (kHidE + 1), k = i % (kHidE + 1);
+      float a = 0.f;
+      if (k < kHidE) {
+        for (int f = 0; f < F; ++f) a = fmaf(dgb[m * F + f], fmaxf(pre[k * F + f], 0.f), a);
+        dw2[m * kHidE + k] += a;
+      } else {
+        for (int f = 0; f < F; ++f) a += dgb[m * F + f];
+        db2[m] += a;
+      }
+    }
+    for (int i = tid; i < kHidE * F; i += blockDim.x) {
+      const int k = i / F, f = i % F;
+      float a = 0.f;
+      for (int m = 0; m < 2 * C; ++m) a = fmaf(w2[m * kHidE + k], dgb[m * F + f], a);
+      dh[i] = pre[i] > 0.f ? a : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < kHidE * (kPe + 1); i += blockDim.x) {       // dW0 [32][16] and db0 [32]
+      const int k = i / (kPe + 1), j = i % (kPe + 1);
+      float a = 0.f;
+      if (j < kPe) {
+        for (int f = 0; f < F; ++f) a = fmaf(dh[k * F + f], pe[j * F + f], a);
+        dw0[k * kPe + j] += a;
+      } else {
+        for (int f = 0; f < F; ++f) a += dh[k * F + f];
+        db0[k] += a;
+      }
+    }
+  }
+  if (mask && tid == 0) {
+    const int L = F / 2 + 1;
+    const float sc = scale[0];
+    float ds = 0.f;
+    for (int l = 0; l < L; ++l) {
+      float dm = 0.f;
+      for (int t = 0; t < F; ++t)
+        dm += dkfg[t] * cospif(2.f * static_cast<float>((l * t) % F) / static_cast<float>(F));
+      dm *= irfft_weight(l, F) / static_cast<float>(F);
+      dmask[l] += dm * sc;
+      ds += dm * mask[l];
+    }
+    dscale[0] += ds;
+  }
+}
+
 }  // namespace
 }  // namespace spff
 
@@ -477,6 +614,41 @@ int spff_gate_micro_bwd(const float* R, const float* S, const float* coef, const
   if (smem > 48 * 1024)
     SPFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<s.n, spff::kT, smem, static_cast<cudaStream_t>(stream)>>>(a, R, coef, gamma, o);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* Gate tables from the parameters (EnergyFiLM3D MLP over the sinusoidal bin code, models.py:1494-1512; FourierGate3D
+ * kernel irfft(freq_mask * mag_scale), models.py:1537-1542). Either group of pointers may be NULL (variant without that gate). */
+int spff_gate_tables_fwd(const float* w0, const float* b0, const float* w2, const float* b2, const float* freq_mask,
+                         const float* mag_scale, int c, int frames, float* g1, float* bt, float* kfg, void* stream) {
+  int e = spff_device_check();
+  if (e) return e;
+  SPFF_REQUIRE(c > 0 && frames > 0 && frames <= spff::kMaxF, "gate_tables_fwd: 0 < frames <= %d, got %d", spff::kMaxF, frames);
+  SPFF_REQUIRE(!w0 || (b0 && w2 && b2 && g1 && bt), "gate_tables_fwd: EFiLM needs all of w0 b0 w2 b2 g1 bt");
+  SPFF_REQUIRE(!freq_mask || (mag_scale && kfg), "gate_tables_fwd: FourierGate needs freq_mask, mag_scale, kfg");
+  if (!w0 && !freq_mask) return 0;
+  spff::gate_tables_fwd_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(w0, b0, w2, b2, freq_mask, mag_scale, c, frames,
+                                                                                  g1, bt, kfg);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+/* Their backward: the parameter gradients are ACCUMULATED (+=) from the table gradients the gate kernels summed. */
+int spff_gate_tables_bwd(const float* w0, const float* b0, const float* w2, const float* b2, const float* freq_mask,
+                         const float* mag_scale, int c, int frames, const float* dg1, const float* dbt, const float* dkfg,
+                         float* dw0, float* db0, float* dw2, float* db2, float* dfreq_mask, float* dmag_scale, void* stream) {
+  int e = spff_device_check();
+  if (e) return e;
+  SPFF_REQUIRE(c > 0 && frames > 0 && frames <= spff::kMaxF, "gate_tables_bwd: 0 < frames <= %d, got %d", spff::kMaxF, frames);
+  SPFF_REQUIRE(!w0 || (b0 && w2 && b2 && dg1 && dbt && dw0 && db0 && dw2 && db2), "gate_tables_bwd: EFiLM pointers incomplete");
+  SPFF_REQUIRE(!freq_mask || (mag_scale && dkfg && dfreq_mask && dmag_scale), "gate_tables_bwd: FourierGate pointers incomplete");
+  if (!w0 && !freq_mask) return 0;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(spff::kPe) * frames + 2 * spff::kHidE * frames + 2 * static_cast<size_t>(c) * frames);
+  auto kern = spff::gate_tables_bwd_kernel;
+  if (smem > 48 * 1024) SPFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<1, 256, smem, static_cast<cudaStream_t>(stream)>>>(w0, b0, w2, b2, freq_mask, mag_scale, c, frames, dg1, dbt, dkfg, dw0, db0,
+                                                           dw2, db2, dfreq_mask, dmag_scale);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }

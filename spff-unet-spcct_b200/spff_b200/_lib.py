@@ -67,6 +67,8 @@ _PROTOTYPES = {
     "spff_norm_act_reduce_workspace": [c_int, Shape],
     "spff_norm_act_reduce": [_P, _LL, _P, _P, c_int, Shape, c_float, _P, c_size_t, _P],
     "spff_norm_act_affine_apply": [_P, _LL, _P, _P, _P, _P, _LL, _P, _LL, c_int, Shape, c_float, _P],
+    "spff_gate_tables_fwd": [_P] * 6 + [c_int, c_int] + [_P] * 3 + [_P],
+    "spff_gate_tables_bwd": [_P] * 6 + [c_int, c_int] + [_P] * 9 + [_P],
     "spff_gate_micro_fwd": [_P] * 8 + [c_int, c_int, c_int, Shape, _P, _P, _P],
     "spff_norm_act_bwd_reduce_workspace": [c_int, Shape, c_int],
     "spff_norm_act_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, _P, c_int, Shape, c_float, c_int, _P, c_size_t, _P],
@@ -82,6 +84,9 @@ _PROTOTYPES = {
     "spff_head_loss_workspace": [c_int],
     "spff_head_loss_fused": [_P, _LL, c_int, _P, _P, _P, c_int, c_int, c_int, Shape, _P, _P, _P, _P, _P, _P, _LL, _P, _P,
                              c_float, _P, c_size_t, _P],
+    "spff_count_valid": [_P, c_int, _LL, c_int, _P, _P],
+    "spff_loss_from_tally": [_P, _P, _P, c_int, c_double, _P, _P],
+    "spff_partial_colsum": [_P, _LL, _LL, c_int, _P, _P],
     "spff_adam_step": [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_int, c_float, _P],
     "spff_pack_convt_weight_k222": [_P, _P, _P, c_int, c_int, _P],
     "spff_convt_k222_fwd": [_P, _LL, c_int, _P, _P, _P, _LL, c_int, Shape, _P],

@@ -32,7 +32,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 
-from . import ops, tables
+from . import ops
 from ._lib import Shape
 
 GATE_EFILM, GATE_FOURIER, GATE_SPECSE, GATE_CHANSE = 1, 2, 4, 8
@@ -178,16 +178,16 @@ class _GroupBuffers:
 
 
 class GateTables:
-    """Per-step parameter-only tensors of the gates (tables.py) plus their gradient accumulators.
+    """Per-step parameter-only tensors of the gates plus their gradient accumulators.
 
-    The tables are built from detached leaf copies of the EFiLM MLP / FourierGate parameters, so
-    that `finish()` can push the accumulated table gradients through the few torch ops of tables.py
-    without touching the caller's autograd graph."""
-
-    _TABLE_PARAMS = ("efilm.mlp.0.weight", "efilm.mlp.0.bias", "efilm.mlp.2.weight", "efilm.mlp.2.bias",
-                     "fgate.freq_mask", "fgate.mag_scale")
+    EnergyFiLM's (g1, bt) [C,F] come from an MLP over a constant sinusoidal code of the bin index (reference
+    models.py:1494-1512) and FourierGate's mask acts as a circular convolution with kernel kfg [F] = irfft(freq_mask *
+    mag_scale) (models.py:1537-1542): both depend on parameters only. One kernel per block builds them
+    (spff_gate_tables_fwd), the gate kernels accumulate the table gradients (dg1, dbt, dkfg) over the sample groups, and
+    `finish()` folds those into the parameter gradients with one kernel per block (spff_gate_tables_bwd)."""
 
     def __init__(self, cfg: NetConfig, params: Dict[str, torch.Tensor], frames: int, need_grad: bool):
+        self.cfg, self.params, self.frames = cfg, params, frames
         self.g1: Dict[str, Optional[torch.Tensor]] = {}
         self.bt: Dict[str, Optional[torch.Tensor]] = {}
         self.kfg: Dict[str, Optional[torch.Tensor]] = {}
@@ -195,64 +195,68 @@ class GateTables:
         self.dg1: Dict[str, Optional[torch.Tensor]] = {}
         self.dbt: Dict[str, Optional[torch.Tensor]] = {}
         self.dkfg: Dict[str, Optional[torch.Tensor]] = {}
-        self.leaves: Dict[str, torch.Tensor] = {}
-        self._live: Dict[str, List[torch.Tensor]] = {b: [] for b in BLOCKS}    # tables with a graph, per block,
-        self._grads: Dict[str, List[torch.Tensor]] = {b: [] for b in BLOCKS}   # paired with their gradient accumulators
-        self._leaf_block: Dict[str, str] = {}
         self._done: set = set()
+        dev = next(iter(params.values())).device
+        # one allocation for the tables, one zero-filled allocation for their gradient accumulators
+        sizes = {b: cfg.channels(b)[1] * frames for b in BLOCKS}
+        per = {b: (2 * sizes[b] if cfg.efilm else 0) + (frames if cfg.fgate else 0) for b in BLOCKS}
+        total = sum((v + 3) // 4 * 4 for v in per.values())
+        tab = torch.empty(max(total, 4), device=dev)
+        acc = torch.zeros(max(total, 4), device=dev) if need_grad else None
+        off = 0
+        for b in BLOCKS:
+            c = cfg.channels(b)[1]
+            self.g1[b] = self.bt[b] = self.kfg[b] = self.se[b] = None
+            self.dg1[b] = self.dbt[b] = self.dkfg[b] = None
+            o = off
 
-        def leaf(name):
-            t = params[name].detach()
-            if need_grad:
-                t = t.clone().requires_grad_(True)
-                self.leaves[name] = t
-                self._leaf_block[name] = name.split(".")[0]
-            return t
+            def take(n, shape):
+                nonlocal o
+                t = tab[o:o + n].view(shape)
+                a = acc[o:o + n].view(shape) if acc is not None else None
+                o += n
+                return t, a
+            if cfg.efilm:
+                self.g1[b], self.dg1[b] = take(sizes[b], (c, frames))
+                self.bt[b], self.dbt[b] = take(sizes[b], (c, frames))
+            if cfg.fgate:
+                self.kfg[b], self.dkfg[b] = take(frames, (frames,))
+            off += (per[b] + 3) // 4 * 4
+            if cfg.efilm or cfg.fgate:
+                ops.gate_tables_fwd(*self._table_params(b), c, frames, self.g1[b], self.bt[b], self.kfg[b])
+            if cfg.chanse and b in _STAGE:
+                i = _STAGE[b]
+                w1 = params[f"se.{i}.fc.0.weight"]
+                w2 = params[f"se.{i}.fc.2.weight"]
+                self.se[b] = (w1.reshape(w1.shape[0], w1.shape[1]), params[f"se.{i}.fc.0.bias"],
+                              w2.reshape(w2.shape[0], w2.shape[1]), params[f"se.{i}.fc.2.bias"])
 
-        with torch.set_grad_enabled(need_grad):
-            for b in BLOCKS:
-                c = cfg.channels(b)[1]
-                self.g1[b] = self.bt[b] = self.kfg[b] = self.se[b] = None
-                self.dg1[b] = self.dbt[b] = self.dkfg[b] = None
-                if cfg.efilm:
-                    g1, bt = tables.efilm_tables(leaf(f"{b}.efilm.mlp.0.weight"), leaf(f"{b}.efilm.mlp.0.bias"),
-                                                 leaf(f"{b}.efilm.mlp.2.weight"), leaf(f"{b}.efilm.mlp.2.bias"), c, frames)
-                    self.g1[b], self.bt[b] = g1, bt
-                    if need_grad:
-                        self.dg1[b], self.dbt[b] = torch.zeros_like(g1), torch.zeros_like(bt)
-                        self._live[b] += [g1, bt]
-                        self._grads[b] += [self.dg1[b], self.dbt[b]]
-                if cfg.fgate:
-                    k = tables.fourier_kernel(leaf(f"{b}.fgate.freq_mask"), leaf(f"{b}.fgate.mag_scale"), frames)
-                    self.kfg[b] = k
-                    if need_grad:
-                        self.dkfg[b] = torch.zeros_like(k)
-                        self._live[b].append(k)
-                        self._grads[b].append(self.dkfg[b])
-                if cfg.chanse and b in _STAGE:
-                    i = _STAGE[b]
-                    w1 = params[f"se.{i}.fc.0.weight"].detach()
-                    w2 = params[f"se.{i}.fc.2.weight"].detach()
-                    self.se[b] = (w1.reshape(w1.shape[0], w1.shape[1]), params[f"se.{i}.fc.0.bias"].detach(),
-                                  w2.reshape(w2.shape[0], w2.shape[1]), params[f"se.{i}.fc.2.bias"].detach())
+    def _table_params(self, b: str):
+        p, cfg = self.params, self.cfg
+        e = [p[f"{b}.efilm.mlp.0.weight"], p[f"{b}.efilm.mlp.0.bias"], p[f"{b}.efilm.mlp.2.weight"],
+             p[f"{b}.efilm.mlp.2.bias"]] if cfg.efilm else [None] * 4
+        f = [p[f"{b}.fgate.freq_mask"], p[f"{b}.fgate.mag_scale"]] if cfg.fgate else [None] * 2
+        return e + f
 
     @staticmethod
     def _d(t):
-        return t.detach() if t is not None else None
+        return t
 
     def finish(self, G: Dict[str, torch.Tensor], blocks: Optional[Tuple[str, ...]] = None):
         """G[name] += gradient of the EFiLM MLP / FourierGate parameters of `blocks` (default: every block
         not finished yet) from the accumulated table gradients (dg1, dbt, dkfg)."""
-        todo = [b for b in (blocks or BLOCKS) if b not in self._done]
-        live = [t for b in todo for t in self._live[b]]
-        grads = [g for b in todo for g in self._grads[b]]
-        self._done.update(todo)
-        if not live:
+        cfg = self.cfg
+        if not (cfg.efilm or cfg.fgate):
             return
-        torch.autograd.backward(live, grads)
-        for name, t in self.leaves.items():
-            if self._leaf_block[name] in todo and t.grad is not None:
-                G[name].add_(t.grad.view_as(G[name]))
+        for b in (blocks or BLOCKS):
+            if b in self._done:
+                continue
+            self._done.add(b)
+            ge = [G[f"{b}.efilm.mlp.0.weight"], G[f"{b}.efilm.mlp.0.bias"], G[f"{b}.efilm.mlp.2.weight"],
+                  G[f"{b}.efilm.mlp.2.bias"]] if cfg.efilm else [None] * 4
+            gf = [G[f"{b}.fgate.freq_mask"], G[f"{b}.fgate.mag_scale"]] if cfg.fgate else [None] * 2
+            ops.gate_tables_bwd(*self._table_params(b), cfg.channels(b)[1], self.frames, self.dg1[b], self.dbt[b], self.dkfg[b],
+                                *ge, *gf)
 
 
 class SpffEngine:
@@ -454,9 +458,10 @@ class SpffEngine:
     @staticmethod
     def _up_bias_grads(B: _GroupBuffers, G: Dict[str, torch.Tensor]):
         """ConvTranspose3d bias gradient = column sums of dy = the `up` half of the decoder input gradient, summed by the
-        dgrad epilogue per work item (fp32) and folded here in double."""
+        dgrad epilogue per work item (fp32) and folded here in double (spff_partial_colsum)."""
         for l, up in ((3, "up3"), (2, "up2"), (1, "up1")):
-            G[f"{up}.bias"].add_(B.dpartial[l][:, :, 0, :B.C[l]].double().sum((0, 1)).float())
+            dp = B.dpartial[l]                      # [n, slots, 2, 2*C_l]: row (n, slot) holds {sums, sums of squares}
+            ops.partial_colsum(dp, dp.shape[0] * dp.shape[1], 2 * dp.shape[3], B.C[l], G[f"{up}.bias"])
 
     # ------------------------------------------------------------------------------------------
     # batch-level drivers
@@ -614,7 +619,8 @@ class SpffEngine:
             if n_valid is None:   # the CE normaliser spans the whole batch; first needed here
                 if staged is not None:
                     staged.wait_labels()
-                n_valid = (labels != ignore_index).sum().reshape(1)
+                n_valid = tally.n_valid
+                ops.count_valid(labels, ignore_index, n_valid)
             # head + CE + confusion + their backward in one pass; the logits never reach memory
             ops.head_loss_fused(B.out["dec1"], p["out.weight"], p["out.bias"], labels[lo:hi], ignore_index, n_valid, None,
                                 tally.nll, tally.count, tally.confusion, B.gout[1],
@@ -671,25 +677,23 @@ class StagedBatch:
 
 class LossTally:
     """Device-side sufficient statistics of ce_plus_macro_dice_loss and per_class_metrics_3d
-    (helpers.py:668-725, 782-803): sum of nll, number of valid voxels, [label][argmax] tally."""
+    (helpers.py:668-725, 782-803): sum of nll, number of valid voxels, [label][argmax] tally — one 8-byte-element
+    buffer (one memset per step), plus the CE normaliser of the batch and the loss scalar."""
 
     def __init__(self, num_classes: int, device):
         self.k = num_classes
-        self.nll = torch.zeros(1, dtype=torch.float64, device=device)
-        self.count = torch.zeros(1, dtype=torch.int64, device=device)
-        self.confusion = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=device)
+        self._buf = torch.zeros(2 + num_classes * num_classes, dtype=torch.int64, device=device)
+        self.nll = self._buf[0:1].view(torch.float64)
+        self.count = self._buf[1:2]
+        self.confusion = self._buf[2:].view(num_classes, num_classes)
+        self.n_valid = torch.zeros(1, dtype=torch.int64, device=device)
+        self._loss = torch.zeros(1, device=device)
 
     def zero(self):
-        self.nll.zero_()
-        self.count.zero_()
-        self.confusion.zero_()
+        self._buf.zero_()
 
     def loss(self, smooth: float = 1e-6) -> torch.Tensor:
-        """CE + 0.5 * (1 - hard macro Dice over classes 1..K-1) as a device scalar (no host sync)."""
-        cm = self.confusion.double()
-        tp = cm.diagonal()[1:]
-        fp = cm.sum(0)[1:] - tp
-        fn = cm.sum(1)[1:] - tp
-        dice = ((2 * tp + smooth) / (2 * tp + fp + fn + smooth)).mean() if self.k > 1 else cm.new_ones(())
-        ce = self.nll[0] / self.count[0].clamp(min=1).double()
-        return (ce + 0.5 * (1.0 - dice)).float()
+        """CE + 0.5 * (1 - hard macro Dice over classes 1..K-1) as a device scalar (no host sync, one kernel)."""
+        out = torch.empty(1, device=self._buf.device)
+        ops.loss_from_tally(self.nll, self.count, self.confusion, self.k, smooth, out)
+        return out[0]

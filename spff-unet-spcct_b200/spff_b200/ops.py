@@ -231,6 +231,18 @@ def norm_act_affine_apply(x, coef, P, Q, y, ypool, c, slope):
          float(slope), stream_ptr())
 
 
+def gate_tables_fwd(w0, b0, w2, b2, mask, scale, c, frames, g1, bt, kfg):
+    """g1 / bt [c, frames] from the EFiLM MLP, kfg [frames] from the FourierGate mask (None skips a gate)."""
+    call("spff_gate_tables_fwd", ptr(w0), ptr(b0), ptr(w2), ptr(b2), ptr(mask), ptr(scale), c, frames, ptr(g1), ptr(bt), ptr(kfg),
+         stream_ptr())
+
+
+def gate_tables_bwd(w0, b0, w2, b2, mask, scale, c, frames, dg1, dbt, dkfg, dw0, db0, dw2, db2, dmask, dscale):
+    """+= the parameter gradients from the accumulated table gradients."""
+    call("spff_gate_tables_bwd", ptr(w0), ptr(b0), ptr(w2), ptr(b2), ptr(mask), ptr(scale), c, frames, ptr(dg1), ptr(dbt),
+         ptr(dkfg), ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), ptr(dmask), ptr(dscale), stream_ptr())
+
+
 def gate_micro_fwd(S, g1, bt, kfg, se, flags, c, shape, P, Q):
     w1, b1, w2, b2 = se if se is not None else (None, None, None, None)
     hid = w1.shape[0] if w1 is not None else 0
@@ -334,6 +346,20 @@ def head_loss_fused(x, w, b, labels, ignore_index, n_valid, gscale, acc, counts,
     call("spff_head_loss_fused", ptr(x), ldx, 32, ptr(w), ptr(b), ptr(labels), _label_bytes(labels), int(ignore_index), k, s,
          ptr(n_valid), ptr(gscale), ptr(acc), ptr(counts), ptr(confusion), ptr(dx), lddx, ptr(dw), ptr(db), float(beta),
          ptr(ws), ws.numel(), stream_ptr())
+
+
+def count_valid(labels, ignore_index, out):
+    """out (int64 [1]) = number of labels != ignore_index."""
+    call("spff_count_valid", ptr(labels), _label_bytes(labels), labels.numel(), int(ignore_index), ptr(out), stream_ptr())
+
+
+def loss_from_tally(nll, count, confusion, k, smooth, out):
+    call("spff_loss_from_tally", ptr(nll), ptr(count), ptr(confusion), int(k), float(smooth), ptr(out), stream_ptr())
+
+
+def partial_colsum(m, rows, row_stride, cols, out):
+    """out[:cols] += column sums of the [rows, row_stride] fp32 matrix m (first `cols` columns)."""
+    call("spff_partial_colsum", ptr(m), int(rows), int(row_stride), int(cols), ptr(out), stream_ptr())
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
