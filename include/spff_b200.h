@@ -285,7 +285,9 @@ int spff_loss_from_tally(const double* nll, const unsigned long long* count, con
                          double smooth, float* out, void* stream);
 /* out[c] += sum_r m[r * row_stride + c] for c < cols (double accumulation, fixed order): the bias gradient of a
  * ConvTranspose3d from the column sums spff_conv3d_k3_dgrad_stats left per work item (models.py:668-672). */
-int spff_partial_colsum(const float* m, long long rows, long long row_stride, int cols, float* out, void* stream);
+size_t spff_partial_colsum_workspace(int cols);
+int spff_partial_colsum(const float* m, long long rows, long long row_stride, int cols, float* out, void* workspace,
+                        size_t workspace_bytes, void* stream);
 /* ---- optimizer (models.py:591-594: torch.optim.Adam, lr 1e-4, betas (0.9,0.999), eps 1e-8) -------- */
 int spff_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                    float beta1, float beta2, float eps, int step, float grad_scale, void* stream);

@@ -12,11 +12,17 @@ $CMD > $OUT/prof_plain_$TAG.json 2> $OUT/prof_plain_$TAG.err || { echo "plain ru
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launch.log 2>&1
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv3_ -c 1200 --csv \
     --log-file $OUT/conv_traffic_$TAG.csv $CMD > $OUT/ncu_traffic.log 2>&1
-cap() {  # name, kernel regex, skip, count
+cap() {  # name, kernel regex, skip, count. The raw page goes back as CSV; the .ncu-rep files together exceed what gpurun
+         # copies back (64 MiB), so only the halo capture's report is kept (source page).
   ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 -f -o $OUT/prof_$1_$TAG $CMD > $OUT/ncu_$1.log 2>&1
+  ncu -i $OUT/prof_$1_$TAG.ncu-rep --page raw --csv > $OUT/prof_$1_$TAG.csv 2>/dev/null
+  if [ "$1" != "halo" ]; then rm -f $OUT/prof_$1_$TAG.ncu-rep; fi
 }
-cap halo conv3_halo_kernel 0 8
-cap rows conv3_fprop_kernel 0 4
-cap wgrad "conv3_wgrad_kernel" 0 3
-cap wgrad_kh "conv3_wgrad_kh_kernel" 0 2
-ls -la $OUT/*_$TAG.ncu-rep
+cap halo "^conv3_halo_kernel" 0 6
+cap rows "^conv3_fprop_kernel" 0 4
+cap wgrad "^conv3_wgrad_kernel" 0 3
+cap wgrad_kh "^conv3_wgrad_kh_kernel" 0 2
+cap bw_maxpool "^maxpool_bwd_add" 2 1
+cap bw_convt "^pw_gemm_kernel" 0 3
+cap bw_head "^head_loss_mma" 0 1
+ls -la $OUT/ | head -40; du -sh $OUT

@@ -59,23 +59,34 @@ __global__ void loss_from_tally_kernel(const double* __restrict__ nll, const uns
   out[0] = static_cast<float>(nll[0] / static_cast<double>(n) + 0.5 * (1.0 - dice));
 }
 
-// out[c] += sum over `rows` rows of m[r * row_stride + c], c < cols. One block per 32 columns, rows strided over the
-// block's warps, double accumulation, fixed reduction order.
-__global__ void partial_colsum_kernel(const float* __restrict__ m, long long rows, long long row_stride, int cols,
-                                      float* __restrict__ out) {
+// out[c] += sum over `rows` rows of m[r * row_stride + c], c < cols, in two fixed-order stages: kColChunks row chunks per
+// 32 columns (double partials in the workspace), then one block folds the chunks in order.
+constexpr int kColChunks = 128;
+
+__global__ void partial_colsum_stage1_kernel(const float* __restrict__ m, long long rows, long long row_stride, int cols,
+                                             double* __restrict__ part /* [kColChunks][cols] */) {
   __shared__ double red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
+  const long long r0 = rows * blockIdx.y / kColChunks, r1 = rows * (blockIdx.y + 1) / kColChunks;
   double a = 0.0;
   if (c < cols)
-    for (long long r = warp; r < rows; r += 8) a += static_cast<double>(m[r * row_stride + c]);
+    for (long long r = r0 + warp; r < r1; r += 8) a += static_cast<double>(m[r * row_stride + c]);
   red[warp][lane] = a;
   __syncthreads();
   if (warp == 0 && c < cols) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += red[w][lane];
-    out[c] += static_cast<float>(t);
+    part[static_cast<size_t>(blockIdx.y) * cols + c] = t;
   }
+}
+
+__global__ void partial_colsum_stage2_kernel(const double* __restrict__ part, int cols, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double t = 0.0;
+  for (int k = 0; k < kColChunks; ++k) t += part[static_cast<size_t>(k) * cols + c];
+  out[c] += static_cast<float>(t);
 }
 
 }  // namespace
@@ -124,12 +135,22 @@ int spff_loss_from_tally(const double* nll, const unsigned long long* count, con
   return 0;
 }
 
-int spff_partial_colsum(const float* m, long long rows, long long row_stride, int cols, float* out, void* stream) {
+size_t spff_partial_colsum_workspace(int cols) { return static_cast<size_t>(spff::kColChunks) * (cols > 0 ? cols : 0) * sizeof(double); }
+
+int spff_partial_colsum(const float* m, long long rows, long long row_stride, int cols, float* out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
   int e = spff_device_check();
   if (e) return e;
-  SPFF_REQUIRE(m && out && rows >= 0 && cols > 0 && row_stride >= cols, "partial_colsum: bad arguments");
+  SPFF_REQUIRE(m && out && workspace && rows >= 0 && cols > 0 && row_stride >= cols, "partial_colsum: bad arguments");
+  if (workspace_bytes < spff_partial_colsum_workspace(cols)) {
+    spff::set_error("partial_colsum: workspace %zu < %zu bytes", workspace_bytes, spff_partial_colsum_workspace(cols));
+    return SPFF_ERR_WORKSPACE;
+  }
   if (rows == 0) return 0;
-  spff::partial_colsum_kernel<<<(cols + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, rows, row_stride, cols, out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* part = static_cast<double*>(workspace);
+  spff::partial_colsum_stage1_kernel<<<dim3((cols + 31) / 32, spff::kColChunks), 256, 0, st>>>(m, rows, row_stride, cols, part);
+  spff::partial_colsum_stage2_kernel<<<(cols + 127) / 128, 128, 0, st>>>(part, cols, out);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }

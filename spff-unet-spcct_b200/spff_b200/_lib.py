@@ -86,7 +86,8 @@ _PROTOTYPES = {
                              c_float, _P, c_size_t, _P],
     "spff_count_valid": [_P, c_int, _LL, c_int, _P, _P],
     "spff_loss_from_tally": [_P, _P, _P, c_int, c_double, _P, _P],
-    "spff_partial_colsum": [_P, _LL, _LL, c_int, _P, _P],
+    "spff_partial_colsum_workspace": [c_int],
+    "spff_partial_colsum": [_P, _LL, _LL, c_int, _P, _P, c_size_t, _P],
     "spff_adam_step": [_P, _P, _P, _P, _LL, c_float, c_float, c_float, c_float, c_int, c_float, _P],
     "spff_pack_convt_weight_k222": [_P, _P, _P, c_int, c_int, _P],
     "spff_convt_k222_fwd": [_P, _LL, c_int, _P, _P, _P, _LL, c_int, Shape, _P],
@@ -109,7 +110,8 @@ _PROTOTYPES = {
 _SIZE_T_FUNCS = {"spff_conv3d_k3_wgrad_workspace", "spff_conv3d_stem_wgrad_workspace",
                  "spff_convt_k122_wgrad_workspace", "spff_head_bwd_workspace", "spff_head_loss_workspace",
                  "spff_norm_act_reduce_workspace", "spff_norm_act_bwd_reduce_workspace",
-                 "spff_convt_k222_wgrad_workspace", "spff_bn_coeffs_workspace", "spff_grid_aug_workspace"}
+                 "spff_convt_k222_wgrad_workspace", "spff_bn_coeffs_workspace", "spff_grid_aug_workspace",
+                 "spff_partial_colsum_workspace"}
 
 
 def _declare():

@@ -359,7 +359,8 @@ def loss_from_tally(nll, count, confusion, k, smooth, out):
 
 def partial_colsum(m, rows, row_stride, cols, out):
     """out[:cols] += column sums of the [rows, row_stride] fp32 matrix m (first `cols` columns)."""
-    call("spff_partial_colsum", ptr(m), int(rows), int(row_stride), int(cols), ptr(out), stream_ptr())
+    ws = workspace(int(_lib.lib.spff_partial_colsum_workspace(int(cols))), m.device)
+    call("spff_partial_colsum", ptr(m), int(rows), int(row_stride), int(cols), ptr(out), ptr(ws), ws.numel(), stream_ptr())
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):

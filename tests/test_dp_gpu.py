@@ -115,3 +115,36 @@ def test_two_rank_3dunet_step():
     ops.sgd_step(flat, shard[0] + shard[1], buf, 1e-2, 0.99, 0.0, False, True, 0.5)
     assert torch.equal(flat.cpu(), out[0]["flat"])
     assert not torch.equal(out[0]["rm"], out[1]["rm"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_model_on_a_device_that_is_not_the_current_one():
+    """One process, two GPUs: a model moved with plain `.to('cuda:1')` while cuda:0 stays the current device runs on
+    cuda:1's stream with cuda:1 as the launch device (the binding follows its tensors), and both devices can be used in
+    turn (the native per-device caches: shared-memory opt-ins, SM counts). Tensors of two devices in one call raise."""
+    from innovative3D import config as C
+    from oracle import spff_oracle as O
+    from spff_b200 import ops
+    torch.cuda.set_device(0)
+    x, lab = O.phantom_batch(2, 32, 32, seed=5, ignore_frac=0.01)
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        torch.manual_seed(42)
+        lit = dict((v[0], v[1]) for v in C.VARIANTS)["SPFF-UNet"]().to(dev)
+        assert torch.cuda.current_device() == 0
+        with torch.no_grad():
+            logits = lit(x.to(dev))
+        o = lit.fit_step((x.to(dev), lab.to(dev)), optimize=False)
+        torch.cuda.synchronize(dev)
+        assert logits.device == torch.device(dev) and torch.cuda.current_device() == 0
+        outs.append((logits.cpu(), float(o["loss"]), lit._fused["grad"].cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][0], outs[2][0])
+    assert outs[0][1] == outs[1][1]
+    assert float((outs[0][2] - outs[1][2]).norm() / outs[0][2].norm()) < 1e-4     # atomics' ordering only
+    a = torch.zeros(1, 5, 16, 16, 32, dtype=torch.bfloat16, device="cuda:0")
+    b = torch.zeros(1, 5, 16, 16, 32, dtype=torch.bfloat16, device="cuda:1")
+    w = torch.zeros(32, 32, 3, 3, 3, device="cuda:0")
+    wf, _ = ops.pack_conv3_weight(w)
+    with pytest.raises(RuntimeError, match="different devices"):
+        ops.conv3d_k3_fwd(a, 32, wf, b, 32)
+    ops.conv3d_k3_fwd(a, 32, wf, a.clone(), 32)      # the failed call left no stale device record behind
