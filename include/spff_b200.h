@@ -150,8 +150,8 @@ int spff_norm_act_reduce(const void* x, long long ldx, const float* coef, float*
 /* y = lrelu(x*A+B)*P + Q; P,Q are [n][d][c] fp32 or both NULL (identity). If ypool != NULL also
  * writes the (1,2,2) max-pool of y (nn.MaxPool3d, models.py:658-665) to ypool [n,d,h/2,w/2] with pitch ldp. */
 int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, const float* P, const float* Q,
-                               void* y, long long ldy, void* ypool, long long ldp, int c, spff_shape s, float slope,
-                               void* stream);
+                               void* y, long long ldy, void* ypool, long long ldp, uint8_t* pool_argmax, int c, spff_shape s,
+                               float slope, void* stream);
 /* Parameter-only tables of the gates and their backward (EnergyFiLM3D models.py:1494-1512: g1 = 1 + tanh(gamma), bt = beta,
  * each [c][frames], from the MLP weights w0 [32][16], b0 [32], w2 [2c][32], b2 [2c] over the sinusoidal bin code;
  * FourierGate3D models.py:1537-1542: kfg [frames] = irfft(freq_mask [frames/2+1] * mag_scale [1])). A NULL w0 / freq_mask
@@ -197,6 +197,10 @@ int spff_norm_act_bwd_apply(const void* dout, long long lddo, const void* x, lon
  * scatter(dpool) at the arg-max of y in each 2x2 window (first max wins, as ATen). `s` = full-res grid. */
 int spff_maxpool_bwd_add(const void* dpool, long long ldp, const void* y, long long ldy, void* dskip, long long ldd,
                          int c, spff_shape s, int accumulate, void* stream);
+/* The same from the arg-max codes spff_norm_act_affine_apply wrote beside the pooled tensor (pool_argmax: uint8
+ * [n,d,h/2,w/2,c], the corner 0..3 = (kh,kw) of the window's first maximum): the full-resolution activation is not read. */
+int spff_maxpool_bwd_add_argmax(const void* dpool, long long ldp, const uint8_t* pool_argmax, void* dskip, long long ldd,
+                                int c, spff_shape s, int accumulate, void* stream);
 
 /* ---- head (1x1x1 conv + bias, models.py:674) and loss (helpers.py:782-803) ------------------------ */
 /* logits fp32 [N,K,D,H,W] = x[pos][0..32) . w[K][32] + b[K]   (cin must be 32, K <= 16). */

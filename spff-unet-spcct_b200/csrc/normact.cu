@@ -370,8 +370,8 @@ template <bool AFFINE>
 __global__ void __launch_bounds__(kBlock)
 norm_act_pool_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const float* __restrict__ coef,
                      const float* __restrict__ P, const float* __restrict__ Q, __nv_bfloat16* __restrict__ y,
-                     long long ldy, __nv_bfloat16* __restrict__ yp, long long ldp, PlaneGrid g, int d, int c, int h,
-                     int w, float slope) {
+                     long long ldy, __nv_bfloat16* __restrict__ yp, long long ldp, uint8_t* __restrict__ argmax, PlaneGrid g,
+                     int d, int c, int h, int w, float slope) {
   const int n = blockIdx.z, dd = blockIdx.y;
   const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
   const int w2 = w / 2;
@@ -390,6 +390,7 @@ norm_act_pool_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const f
   for (int p = p0 + r; p < p1; p += g.rpi) {
     const int hp = p / w2, wp = p % w2;
     float mx[8];
+    uint32_t code[2] = {0u, 0u};    // per channel: which corner of the window holds the (first) maximum, one byte each
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const long long pos = base + static_cast<long long>(2 * hp + (k >> 1)) * w + 2 * wp + (k & 1);
@@ -405,9 +406,17 @@ norm_act_pool_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const f
       stg16(y + pos * ldy + v * 8, o);
       unpack8(o, f);  // pool the values as stored (bf16), so that backward finds the same arg-max
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mx[i] = (k == 0) ? f[i] : fmaxf(mx[i], f[i]);
+      for (int i = 0; i < 8; ++i) {
+        if (k == 0) {
+          mx[i] = f[i];
+        } else if (f[i] > mx[i]) {   // strict: the first maximum in (kh, kw) order wins, as in max_pool backward
+          mx[i] = f[i];
+          code[i >> 2] = (code[i >> 2] & ~(0xffu << (8 * (i & 3)))) | (static_cast<uint32_t>(k) << (8 * (i & 3)));
+        }
+      }
     }
     stg16(yp + (basep + p) * ldp + v * 8, pack8(mx));
+    if (argmax) *reinterpret_cast<uint2*>(argmax + (basep + p) * c + v * 8) = make_uint2(code[0], code[1]);
   }
 }
 
@@ -564,6 +573,54 @@ norm_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long lddo
         }
         stg16(dx + (base + p + u * g.rpi) * lddx + v * 8, pack8(f));
       }
+    }
+  }
+}
+
+// The same from the arg-max codes the forward wrote (one byte per pooled element: corner 0..3 of its window): the
+// full-resolution activation is not read again (a third of this kernel's traffic; half-line reads of the 2C-pitch concat
+// buffer are fetched as whole lines, so more than a third at level 1).
+__global__ void __launch_bounds__(kBlock)
+maxpool_bwd_codes_kernel(const __nv_bfloat16* __restrict__ dpool, long long ldp, const uint8_t* __restrict__ argmax,
+                         __nv_bfloat16* __restrict__ dskip, long long ldd, PlaneGrid g, int d, int c, int h, int w,
+                         int accumulate) {
+  const int n = blockIdx.z, dd = blockIdx.y;
+  const int v = threadIdx.x % g.c8, r = threadIdx.x / g.c8;
+  const int w2 = w / 2;
+  const long long base = (static_cast<long long>(n) * d + dd) * (static_cast<long long>(h) * w);
+  const long long basep = (static_cast<long long>(n) * d + dd) * g.hw;
+  const int p0 = blockIdx.x * g.chunk;
+  const int p1 = min(g.hw, p0 + g.chunk);
+  if (r >= g.rpi) return;
+  const long long od[4] = {0, ldd, static_cast<long long>(w) * ldd, static_cast<long long>(w + 1) * ldd};
+  __nv_bfloat16* db = dskip + base * ldd + v * 8;
+  for (int p = p0 + r; p < p1; p += g.rpi) {
+    const int hp = p / w2, wp = p % w2;
+    __nv_bfloat16* dc = db + (static_cast<long long>(2 * hp) * w + 2 * wp) * ldd;
+    const uint4 rawg = ldg16(dpool + (basep + p) * ldp + v * 8);
+    const uint2 cd = __ldg(reinterpret_cast<const uint2*>(argmax + (basep + p) * c + v * 8));
+    uint4 rawd[4];
+    if (accumulate) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rawd[k] = *reinterpret_cast<const uint4*>(dc + od[k]);
+    }
+    float gp[8];
+    unpack8(rawg, gp);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+      if (accumulate) {
+        unpack8(rawd[k], o);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t a = ((i < 4 ? cd.x : cd.y) >> (8 * (i & 3))) & 0xffu;
+        o[i] += (a == static_cast<uint32_t>(k)) ? gp[i] : 0.f;
+      }
+      stg16(dc + od[k], pack8(o));
     }
   }
 }
@@ -1120,8 +1177,8 @@ int spff_norm_act_reduce(const void* x, long long ldx, const float* coef, float*
 }
 
 int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, const float* P, const float* Q,
-                               void* y, long long ldy, void* ypool, long long ldp, int c, spff_shape s, float slope,
-                               void* stream) {
+                               void* y, long long ldy, void* ypool, long long ldp, uint8_t* pool_argmax, int c, spff_shape s,
+                               float slope, void* stream) {
   SPFF_ENTRY_CHECK();
   SPFF_REQUIRE((P == nullptr) == (Q == nullptr), "norm_act_affine_apply: P and Q must both be given or both be NULL");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1134,11 +1191,11 @@ int spff_norm_act_affine_apply(const void* x, long long ldx, const float* coef, 
     if (P)
       spff::norm_act_pool_kernel<true><<<grid, kBlock, 0, st>>>(static_cast<const bf16*>(x), ldx, coef, P, Q,
                                                                static_cast<bf16*>(y), ldy, static_cast<bf16*>(ypool),
-                                                               ldp, g, s.d, c, s.h, s.w, slope);
+                                                               ldp, pool_argmax, g, s.d, c, s.h, s.w, slope);
     else
       spff::norm_act_pool_kernel<false><<<grid, kBlock, 0, st>>>(static_cast<const bf16*>(x), ldx, coef, P, Q,
                                                                 static_cast<bf16*>(y), ldy, static_cast<bf16*>(ypool),
-                                                                ldp, g, s.d, c, s.h, s.w, slope);
+                                                                ldp, pool_argmax, g, s.d, c, s.h, s.w, slope);
   } else {
     int e = spff::make_grid(c, static_cast<long long>(s.h) * s.w, s, &g, &grid, 32);
     if (e) return e;
@@ -1267,6 +1324,22 @@ int spff_maxpool_bwd_add(const void* dpool, long long ldp, const void* y, long l
   spff::maxpool_bwd_add_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(dpool), ldp, static_cast<const bf16*>(y), ldy, static_cast<bf16*>(dskip), ldd, g, s.d,
       s.h, s.w, accumulate);
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_maxpool_bwd_add_argmax(const void* dpool, long long ldp, const uint8_t* pool_argmax, void* dskip, long long ldd,
+                                int c, spff_shape s, int accumulate, void* stream) {
+  SPFF_ENTRY_CHECK();
+  SPFF_REQUIRE(dpool && pool_argmax && dskip, "maxpool_bwd_add_argmax: null pointer");
+  SPFF_REQUIRE(s.h % 2 == 0 && s.w % 2 == 0, "maxpool_bwd_add_argmax: needs even H, W");
+  SPFF_REQUIRE(c % 8 == 0 && (reinterpret_cast<uintptr_t>(pool_argmax) & 7) == 0, "maxpool_bwd_add_argmax: c %% 8 and 8-byte aligned codes");
+  PlaneGrid g;
+  dim3 grid;
+  int e = spff::make_grid(c, static_cast<long long>(s.h / 2) * (s.w / 2), s, &g, &grid, 32);
+  if (e) return e;
+  spff::maxpool_bwd_codes_kernel<<<grid, kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(dpool), ldp, pool_argmax, static_cast<bf16*>(dskip), ldd, g, s.d, c, s.h, s.w, accumulate);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -66,7 +66,7 @@ _PROTOTYPES = {
     "spff_norm_act_apply": [_P, _LL, _P, _P, _LL, c_int, Shape, c_float, _P],
     "spff_norm_act_reduce_workspace": [c_int, Shape],
     "spff_norm_act_reduce": [_P, _LL, _P, _P, c_int, Shape, c_float, _P, c_size_t, _P],
-    "spff_norm_act_affine_apply": [_P, _LL, _P, _P, _P, _P, _LL, _P, _LL, c_int, Shape, c_float, _P],
+    "spff_norm_act_affine_apply": [_P, _LL, _P, _P, _P, _P, _LL, _P, _LL, _P, c_int, Shape, c_float, _P],
     "spff_gate_tables_fwd": [_P] * 6 + [c_int, c_int] + [_P] * 3 + [_P],
     "spff_gate_tables_bwd": [_P] * 6 + [c_int, c_int] + [_P] * 9 + [_P],
     "spff_gate_micro_fwd": [_P] * 8 + [c_int, c_int, c_int, Shape, _P, _P, _P],
@@ -75,6 +75,7 @@ _PROTOTYPES = {
     "spff_gate_micro_bwd": [_P] * 11 + [c_int, c_int, c_int, Shape] + [_P] * 12 + [_P],
     "spff_norm_act_bwd_apply": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _LL, c_int, Shape, c_float, _P],
     "spff_maxpool_bwd_add": [_P, _LL, _P, _LL, _P, _LL, c_int, Shape, c_int, _P],
+    "spff_maxpool_bwd_add_argmax": [_P, _LL, _P, _P, _LL, c_int, Shape, c_int, _P],
     "spff_head_fwd": [_P, _LL, c_int, _P, _P, _P, c_int, Shape, _P],
     "spff_head_argmax": [_P, _LL, c_int, _P, _P, _P, c_int, Shape, _P],
     "spff_head_bwd_workspace": [c_int],

@@ -116,6 +116,10 @@ class _GroupBuffers:
         self.HW = {l: (h >> (l - 1), w >> (l - 1)) for l in (1, 2, 3, 4)}
         self.cat = {l: bf(*self.HW[l], 2 * self.C[l]) for l in (1, 2, 3)}
         self.pool = {l: bf(*self.HW[l + 1], self.C[l]) for l in (1, 2, 3)}    # pooled output of level l
+        # training: which corner of each pooling window held the maximum (one byte per pooled element), so that the
+        # backward need not read the full-resolution activation again
+        self.pool_argmax = {l: torch.empty(n, d, *self.HW[l + 1], self.C[l], dtype=torch.uint8, device=device)
+                            for l in (1, 2, 3)} if train else {l: None for l in (1, 2, 3)}
         self.x1, self.a1, self.x2, self.out = {}, {}, {}, {}
         self.partial: Dict[str, torch.Tensor] = {}
         self.slots: Dict[str, int] = {}
@@ -346,7 +350,8 @@ class SpffEngine:
             ops.norm_act_reduce(B.x2[b], B.coef[f"{b}.2"], S, c, SLOPE, fixed_order=True)
             P, Q = B.P[b], B.Q[b]
             ops.gate_micro_fwd(S, T._d(T.g1[b]), T._d(T.bt[b]), T._d(T.kfg[b]), T.se[b], flags, c, shp, P, Q)
-        ops.norm_act_affine_apply(B.x2[b], B.coef[f"{b}.2"], P, Q, B.out[b], pool_to, c, SLOPE)
+        ops.norm_act_affine_apply(B.x2[b], B.coef[f"{b}.2"], P, Q, B.out[b], pool_to, c, SLOPE,
+                                  pool_argmax=B.pool_argmax[l] if pool_to is not None else None)
 
     def forward_group(self, B: _GroupBuffers, T: GateTables, x: torch.Tensor, head: str = "logits",
                       logits_out: Optional[torch.Tensor] = None, labels_out: Optional[torch.Tensor] = None):
@@ -445,7 +450,7 @@ class SpffEngine:
         for l, enc in ((3, "enc3"), (2, "enc2"), (1, "enc1")):
             c = B.C[l]
             dskip = B.dcat[l][..., c:]
-            ops.maxpool_bwd_add(B.dpool[l], B.out[enc], dskip, c, True)
+            ops.maxpool_bwd_add_argmax(B.dpool[l], B.pool_argmax[l], dskip, c, True)
             if l > 1:
                 self._block_bwd(B, T, G, enc, dskip, B.pool[l - 1], B.dpool[l - 1])
             else:

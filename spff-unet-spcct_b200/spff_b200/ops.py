@@ -223,11 +223,16 @@ def norm_act_reduce(x, coef, S, c, slope, fixed_order=False):
          stream_ptr())
 
 
-def norm_act_affine_apply(x, coef, P, Q, y, ypool, c, slope):
+def norm_act_affine_apply(x, coef, P, Q, y, ypool, c, slope, pool_argmax=None):
+    """pool_argmax: optional uint8 [n,d,h/2,w/2,c] (contiguous) receiving the corner 0..3 of every pooling window's first
+    maximum, for maxpool_bwd_add_argmax."""
     s, ldx = _view(x, c)
     _, ldy = _view(y, c)
     ldp = _view(ypool, c)[1] if ypool is not None else 0
-    call("spff_norm_act_affine_apply", ptr(x), ldx, ptr(coef), ptr(P), ptr(Q), ptr(y), ldy, ptr(ypool), ldp, c, s,
+    if pool_argmax is not None:
+        assert ypool is not None and pool_argmax.dtype == torch.uint8 and pool_argmax.is_contiguous()
+        assert tuple(pool_argmax.shape) == (s.n, s.d, s.h // 2, s.w // 2, c)
+    call("spff_norm_act_affine_apply", ptr(x), ldx, ptr(coef), ptr(P), ptr(Q), ptr(y), ldy, ptr(ypool), ldp, ptr(pool_argmax), c, s,
          float(slope), stream_ptr())
 
 
@@ -286,6 +291,14 @@ def maxpool_bwd_add(dpool, y, dskip, c, accumulate):
     _, ldp = _view(dpool, c)
     _, ldd = _view(dskip, c)
     call("spff_maxpool_bwd_add", ptr(dpool), ldp, ptr(y), ldy, ptr(dskip), ldd, c, s, int(accumulate), stream_ptr())
+
+
+def maxpool_bwd_add_argmax(dpool, pool_argmax, dskip, c, accumulate):
+    """dskip[window corner pool_argmax] += dpool, without reading the full-resolution activation."""
+    s, ldd = _view(dskip, c)
+    _, ldp = _view(dpool, c)
+    assert pool_argmax.dtype == torch.uint8 and pool_argmax.is_contiguous()
+    call("spff_maxpool_bwd_add_argmax", ptr(dpool), ldp, ptr(pool_argmax), ptr(dskip), ldd, c, s, int(accumulate), stream_ptr())
 
 
 # ------------------------------------------------------------------------------------------------

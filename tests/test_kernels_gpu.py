@@ -248,6 +248,17 @@ def test_pool_fwd_bwd():
     sb2 = torch.full_like(sb, float("nan"))
     ops.maxpool_bwd_add(dpb, y, sb2, c, False)
     assert rel(ncdhw(sb2), yr.grad) < 1e-6
+    # the arg-max codes written by the forward give the same backward without reading y (ties included: y is bf16)
+    codes = torch.full((n, d, h // 2, w // 2, c), 255, dtype=torch.uint8, device="cuda")
+    y3, yp3 = torch.empty_like(xb), torch.empty_like(yp)
+    ops.norm_act_affine_apply(xb, coef, None, None, y3, yp3, c, 0.01, pool_argmax=codes)
+    assert torch.equal(y3, y) and torch.equal(yp3, yp) and int(codes.max()) <= 3
+    sb3 = torch.full_like(sb, float("nan"))
+    ops.maxpool_bwd_add_argmax(dpb, codes, sb3, c, False)
+    assert torch.equal(sb3, sb2)
+    sb4 = pm(skip)
+    ops.maxpool_bwd_add_argmax(dpb, codes, sb4, c, True)
+    assert torch.equal(sb4, sb)
 
 
 @pytest.mark.parametrize("n,d,h,w", [(2, 5, 16, 16), (1, 5, 7, 9), (1, 3, 4, 4), (1, 5, 8, 136), (2, 5, 128, 128)])
