@@ -442,10 +442,15 @@ conv3_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         }
         if (row_out) {
           __nv_bfloat16* dst = p.y + ((static_cast<long long>(n) * p.d + d) * p.hw + q) * p.ldy + cb * kCoBlk;
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
+          if ((p.ldy & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0) {   // 32-byte aligned rows: full-sector stores
+            st_global_v8(dst, packed[0], packed[1], packed[2], packed[3], packed[4], packed[5], packed[6], packed[7]);
+            st_global_v8(dst + 16, packed[8], packed[9], packed[10], packed[11], packed[12], packed[13], packed[14], packed[15]);
+          } else {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
-            d4[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+            for (int v = 0; v < 4; ++v)
+              d4[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+          }
         }
         xpar ^= 1;
       }

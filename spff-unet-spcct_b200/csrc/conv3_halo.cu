@@ -380,10 +380,17 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         __nv_bfloat16* dst =
             p.y + (((static_cast<long long>(n) * p.d + d) * p.h + h) * p.w + w) * p.ldy + cb * CO;
-        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        if ((p.ldy & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0) {   // 32-byte aligned rows: one full sector per store instead of two halves
 #pragma unroll
-        for (int q = 0; q < CO / 8; ++q)
-          d4[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+          for (int q = 0; q < CO / 16; ++q)
+            st_global_v8(dst + 16 * q, packed[8 * q], packed[8 * q + 1], packed[8 * q + 2], packed[8 * q + 3], packed[8 * q + 4],
+                         packed[8 * q + 5], packed[8 * q + 6], packed[8 * q + 7]);
+        } else {
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int q = 0; q < CO / 8; ++q)
+            d4[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
       }
       if constexpr (STATS) {
         // item totals: columns across the 32 rows of each warp, then across the 4 warps through shared memory

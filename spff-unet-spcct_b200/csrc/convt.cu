@@ -209,9 +209,14 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
               }
               pk[c >> 1] = pack_bf16x2(a, b);
             }
-            uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
+            if ((p.ldo & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0) {   // 32-byte aligned rows: full-sector stores
+              st_global_v8(dst + c0, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+              st_global_v8(dst + c0 + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+            } else {
+              uint4* d4 = reinterpret_cast<uint4*>(dst + c0);
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) d4[qq] = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+              for (int qq = 0; qq < 4; ++qq) d4[qq] = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+            }
           }
         }
       }
