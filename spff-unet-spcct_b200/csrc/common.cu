@@ -136,9 +136,9 @@ TileGeom make_tile_geom(const int ext[4], int rows) {
 
 static int g_debug_ctas = 0;
 int debug_ctas() { return g_debug_ctas; }
-static long long g_debug_flags[8] = {0};
-int debug_flag(int key) { return (key >= 0 && key < 8) ? static_cast<int>(g_debug_flags[key]) : 0; }
-long long debug_value(int key) { return (key >= 0 && key < 8) ? g_debug_flags[key] : 0; }
+static long long g_debug_flags[16] = {0};
+int debug_flag(int key) { return (key >= 0 && key < 16) ? static_cast<int>(g_debug_flags[key]) : 0; }
+long long debug_value(int key) { return (key >= 0 && key < 16) ? g_debug_flags[key] : 0; }
 
 }  // namespace spff
 
@@ -171,7 +171,7 @@ int spff_debug_set(int key, long long value) {
     spff::g_debug_ctas = static_cast<int>(value);
     return 0;
   }
-  if (key > 0 && key < 8) {
+  if (key > 0 && key < 16) {
     spff::g_debug_flags[key] = value;
     return 0;
   }

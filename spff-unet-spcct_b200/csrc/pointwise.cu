@@ -10,6 +10,7 @@
 // All are bandwidth-bound: one thread per voxel (or per 16-byte channel vector), coalesced
 // accesses, weights broadcast from constant / shared memory.
 #include "common.h"
+#include "ptx.cuh"
 
 #include <cuda_bf16.h>
 
@@ -205,6 +206,194 @@ stem_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     float t = 0.f;
     for (int wp = 0; wp < 8; ++wp) t += red[wp * 2 * cout + idx];
     partial[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 2 * cout + idx] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem forward on the tensor cores (the default of spff_conv3d_stem_fwd_stats): the implicit GEMM
+// M = positions, K = 27 taps (padded to 32), N = 32 channels with warp-level mma.sync m16n8k16. Both
+// operands are split into a bf16 head and a bf16 remainder and the three significant products
+// hi*hi + lo*hi + hi*lo are accumulated in fp32, so the sums carry ~2^-16 relative error (the fp32
+// FMA kernel above: 2^-24; the bf16 rounding of the stored output: 2^-9). A warp owns one segment of
+// <= 128 positions of an image row at a time: it stages the 9 x (128 + 2) input window once (hi and lo
+// planes), gathers the im2col A fragments from it, and transposes each 16 x 32 output tile through
+// shared memory so every lane stores 32 contiguous bytes. Statistics as in the kernel above.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSfWarps = 8;
+constexpr int kSfSeg = 128;                  // positions per segment
+constexpr int kSfPitch = kSfSeg + 2 + 6;     // bf16 per window row
+constexpr int kSfOutPitch = 40;              // bf16 per staged output row (32 + 8 pad: conflict-free)
+constexpr int kSfSmemBytes = (kSfWarps * 2 * 9 * kSfPitch + kSfWarps * 16 * kSfOutPitch) * 2;
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16(v);
+  lo = __float2bfloat16(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_u16(const __nv_bfloat16 a, const __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(kSfWarps * 32, 2)
+stem_fwd_stats_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                          long long ldy, spff_shape s, float* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char sf_smem[];
+  __nv_bfloat16* xs_all = reinterpret_cast<__nv_bfloat16*>(sf_smem);           // [warp][hi/lo][9][kSfPitch]
+  __nv_bfloat16* os_all = xs_all + kSfWarps * 2 * 9 * kSfPitch;                // [warp][16][kSfOutPitch]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  __nv_bfloat16* xh = xs_all + warp * 2 * 9 * kSfPitch;
+  __nv_bfloat16* xl = xh + 9 * kSfPitch;
+  __nv_bfloat16* os = os_all + warp * 16 * kSfOutPitch;
+  // B fragments (K = tap, N = channel), constant for the whole launch; taps >= 27 carry zero weights, so the A
+  // values gathered for them do not matter
+  uint32_t bh[2][4][2], bl[2][4][2];
+  int toff[2][2][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k0 = 16 * ks + 2 * t + 8 * j;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = k0 + e;
+        toff[ks][j][e] = k < 27 ? (k / 3) * kSfPitch + k % 3 : 0;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int n = 8 * nt + g;
+        const float w0 = k0 < 27 ? __ldg(w + n * 27 + k0) : 0.f;
+        const float w1 = k0 + 1 < 27 ? __ldg(w + n * 27 + k0 + 1) : 0.f;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(w0, h0, l0);
+        split_bf16(w1, h1, l1);
+        bh[ks][nt][j] = pack_u16(h0, h1);
+        bl[ks][nt][j] = pack_u16(l0, l1);
+      }
+    }
+  float ssum[4][2], ssq[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) ssum[nt][0] = ssum[nt][1] = ssq[nt][0] = ssq[nt][1] = 0.f;
+  const bool wide = ((ldy & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 31) == 0);
+  const int segs = (s.w + kSfSeg - 1) / kSfSeg;
+  const int nwork = s.d * s.h * segs;                         // of this sample
+  const long long row0 = static_cast<long long>(blockIdx.y) * s.d * s.h;
+  for (int work = blockIdx.x * kSfWarps + warp; work < nwork; work += gridDim.x * kSfWarps) {
+    const int sg = work % segs;
+    const int rw = work / segs;                               // dd*h + hh
+    const int hh = rw % s.h, dd = rw / s.h;
+    const long long row = row0 + rw;
+    const int w0 = sg * kSfSeg;
+    const int wn = min(kSfSeg, s.w - w0);
+    const int wpad = (wn + 15) & ~15;
+    // input window, split: xh/xl[kd*3+kh][c] = x[dd+kd-1][hh+kh-1][w0 + c - 1]
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const int d2 = dd + r / 3 - 1, h2 = hh + r % 3 - 1;
+      const bool rok = d2 >= 0 && d2 < s.d && h2 >= 0 && h2 < s.h;
+      const float* xr = x + (row + static_cast<long long>(r / 3 - 1) * s.h + (r % 3 - 1)) * s.w + w0 - 1;
+      for (int c = lane; c < wpad + 2; c += 32) {
+        const int w2 = w0 + c - 1;
+        const float v = (rok && w2 >= 0 && w2 < s.w) ? __ldg(xr + c) : 0.f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        xh[r * kSfPitch + c] = hi;
+        xl[r * kSfPitch + c] = lo;
+      }
+    }
+    __syncwarp();
+    __nv_bfloat16* yrow = y + (row * s.w + w0) * ldy;
+    for (int mt = 0; mt < wpad / 16; ++mt) {
+      const int p = mt * 16 + g;
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int rh = 0; rh < 2; ++rh) {
+            const int e0 = toff[ks][j][0] + p + 8 * rh, e1 = toff[ks][j][1] + p + 8 * rh;
+            ah[ks][2 * j + rh] = pack_u16(xh[e0], xh[e1]);
+            al[ks][2 * j + rh] = pack_u16(xl[e0], xl[e1]);
+          }
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {   // smallest products first
+          mma_bf16_16816(acc[nt], al[ks], bh[ks][nt]);
+          mma_bf16_16816(acc[nt], ah[ks], bl[ks][nt]);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) mma_bf16_16816(acc[nt], ah[ks], bh[ks][nt]);
+      }
+      const bool ok0 = p < wn, ok1 = p + 8 < wn;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (ok0) {
+          ssum[nt][0] += acc[nt][0];
+          ssum[nt][1] += acc[nt][1];
+          ssq[nt][0] = fmaf(acc[nt][0], acc[nt][0], ssq[nt][0]);
+          ssq[nt][1] = fmaf(acc[nt][1], acc[nt][1], ssq[nt][1]);
+        }
+        if (ok1) {
+          ssum[nt][0] += acc[nt][2];
+          ssum[nt][1] += acc[nt][3];
+          ssq[nt][0] = fmaf(acc[nt][2], acc[nt][2], ssq[nt][0]);
+          ssq[nt][1] = fmaf(acc[nt][3], acc[nt][3], ssq[nt][1]);
+        }
+        *reinterpret_cast<uint32_t*>(&os[g * kSfOutPitch + 8 * nt + 2 * t]) = pack_bf16x2_local(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<uint32_t*>(&os[(g + 8) * kSfOutPitch + 8 * nt + 2 * t]) = pack_bf16x2_local(acc[nt][2], acc[nt][3]);
+      }
+      __syncwarp();
+      {
+        const int pr = lane >> 1, half = lane & 1;
+        if (mt * 16 + pr < wn) {
+          const uint4* src = reinterpret_cast<const uint4*>(&os[pr * kSfOutPitch + half * 16]);
+          const uint4 v0 = src[0], v1 = src[1];
+          __nv_bfloat16* dst = yrow + static_cast<long long>(mt * 16 + pr) * ldy + half * 16;
+          if (wide) {
+            st_global_v8(dst, v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w);
+          } else {
+            *reinterpret_cast<uint4*>(dst) = v0;
+            *reinterpret_cast<uint4*>(dst + 8) = v1;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // lanes with the same t hold the same channels: fold over g by shuffles, then the 8 warps in shared memory
+#pragma unroll
+  for (int off = 4; off <= 16; off <<= 1)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        ssum[nt][e] += __shfl_xor_sync(0xffffffffu, ssum[nt][e], off);
+        ssq[nt][e] += __shfl_xor_sync(0xffffffffu, ssq[nt][e], off);
+      }
+  __syncthreads();                                            // every warp is done with its staging tiles
+  float* red = reinterpret_cast<float*>(os_all);              // [warp][2][32]
+  if (g == 0) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        red[(warp * 2 + 0) * kStemCo + 8 * nt + 2 * t + e] = ssum[nt][e];
+        red[(warp * 2 + 1) * kStemCo + 8 * nt + 2 * t + e] = ssq[nt][e];
+      }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * kStemCo; idx += blockDim.x) {
+    float tot = 0.f;
+    for (int wp = 0; wp < kSfWarps; ++wp) tot += red[wp * 2 * kStemCo + idx];
+    partial[(static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 2 * kStemCo + idx] = tot;
   }
 }
 
@@ -762,11 +951,6 @@ constexpr int kHmBlocksPerSm = 2;
 constexpr int kHmXPitch = 40;   // bf16 per staged x / dx row (32 + 8 pad)
 constexpr int kHmDPitch = 24;   // bf16 per staged dl row (16 + 8 pad)
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
 __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat16 h0 = __float2bfloat16(v0), h1 = __float2bfloat16(v1);
   const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
@@ -1140,6 +1324,19 @@ int spff_conv3d_stem_fwd_stats(const float* x, const float* w, void* y, long lon
   SPFF_REQUIRE(cout == 32, "conv3d_stem_fwd_stats: cout must be 32 (got %d)", cout);
   SPFF_REQUIRE(s.n > 0 && s.n <= 65535 && s.d > 0 && s.h > 0 && s.w > 0, "conv3d_stem_fwd_stats: bad shape");
   dim3 grid(spff_conv3d_stem_stat_slots(s), s.n);
+  if (spff::debug_flag(8) == 0) {   // tensor-core kernel (default); spff_debug_set(8, 1) selects the fp32 FMA kernel
+    static bool attr_set[spff::kMaxDevices] = {};
+    const int dev = spff::current_device();
+    if (!attr_set[dev]) {
+      SPFF_CUDA(cudaFuncSetAttribute(spff::stem_fwd_stats_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     spff::kSfSmemBytes));
+      attr_set[dev] = true;
+    }
+    spff::stem_fwd_stats_mma_kernel<<<grid, spff::kSfWarps * 32, spff::kSfSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+        x, w, static_cast<bf16*>(y), ldy, s, stat_partial);
+    SPFF_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t smem = (27 + 16) * cout * sizeof(float);
   spff::stem_fwd_stats_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, w, static_cast<bf16*>(y), ldy, cout, s,
                                                                                      stat_partial);
