@@ -22,7 +22,8 @@ cap halo "^conv3_halo_kernel" 0 6
 cap rows "^conv3_fprop_kernel" 0 4
 cap wgrad "^conv3_wgrad_kernel" 0 3
 cap wgrad_kh "^conv3_wgrad_kh_kernel" 0 2
-cap bw_maxpool "^maxpool_bwd_add" 2 1
+cap bw_maxpool "^maxpool_bwd_codes" 2 1
 cap bw_convt "^pw_gemm_kernel" 0 3
 cap bw_head "^head_loss_mma" 0 1
+cap stem "^stem_fwd_stats_mma" 0 1
 ls -la $OUT/ | head -40; du -sh $OUT
