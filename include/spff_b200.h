@@ -283,6 +283,10 @@ int spff_sgd_step(float* param, const float* grad, float* momentum_buf, long lon
  * Number of labels != ignore_index (the CE normaliser N_valid of F.cross_entropy, helpers.py:798); labels uint8 or int64. */
 int spff_count_valid(const void* labels, int label_bytes, long long total, int ignore_index, unsigned long long* out,
                      void* stream);
+/* g[i] *= factor / count (0 when count == 0): the fused step back-propagates the SUM of the per-voxel CE terms and divides
+ * the finished gradients by N_valid here (F.cross_entropy's mean reduction, helpers.py:798), so that a group's backward
+ * needs only its own labels on the device, not the whole batch's. */
+int spff_scale_by_count(float* g, long long n, const unsigned long long* count, float factor, void* stream);
 /* ce_plus_macro_dice_loss (helpers.py:782-803) from the tally spff_head_loss_fused / spff_ce_confusion accumulate:
  * out = nll / max(count, 1) + 0.5 * (1 - mean_{c=1..k-1} (2tp+s)/(2tp+fp+fn+s)), confusion [label][argmax]. */
 int spff_loss_from_tally(const double* nll, const unsigned long long* count, const unsigned long long* confusion, int k,

@@ -90,7 +90,7 @@ json.dump({"command": "SPFF_BENCH_SAMPLES=256 python bench.py --steps 1 --warmup
 print(json.dumps(traffic, indent=1))
 
 # 3) --set full captures -------------------------------------------------------------------------------------------
-CAPTURES = ("halo", "rows", "wgrad", "wgrad_kh", "bw_maxpool", "bw_convt", "bw_head") if ROUND == "2" else ("bwd_reduce4", "bwd_apply4", "norm_act", "norm_act_pool", "maxpool_bwd", "wgrad32", "stem", "head_loss")
+CAPTURES = ("halo", "rows", "wgrad", "wgrad_kh", "bw_maxpool", "bw_convt", "bw_head", "stem") if ROUND == "2" else ("bwd_reduce4", "bwd_apply4", "norm_act", "norm_act_pool", "maxpool_bwd", "wgrad32", "stem", "head_loss")
 FULL_NAME = f"profiles/{TAG}_conv_kernels_ncu_full.md" if ROUND == "2" else f"profiles/{TAG}_bandwidth_kernels_ncu_full.md"
 WANT = ["gpu__time_duration.sum", "sm__inst_executed_pipe_tensor.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",

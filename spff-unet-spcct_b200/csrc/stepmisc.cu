@@ -89,6 +89,28 @@ __global__ void partial_colsum_stage2_kernel(const double* __restrict__ part, in
   out[c] += static_cast<float>(t);
 }
 
+// g[i] *= factor / max(count, 1)   (0 when count == 0): the CE normaliser applied to finished gradients
+__global__ void scale_by_count_kernel(float* __restrict__ g, long long n, const unsigned long long* __restrict__ count,
+                                      float factor) {
+  const unsigned long long c = count[0];
+  const float sc = c > 0 ? factor / static_cast<float>(c) : 0.f;
+  const long long n4 = n / 4;
+  float4* g4 = reinterpret_cast<float4*>(g);
+  const bool vec = (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (vec) {
+    for (long long i = i0; i < n4; i += stride) {
+      float4 v = g4[i];
+      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+      g4[i] = v;
+    }
+    for (long long i = n4 * 4 + i0; i < n; i += stride) g[i] *= sc;
+  } else {
+    for (long long i = i0; i < n; i += stride) g[i] *= sc;
+  }
+}
+
 }  // namespace
 }  // namespace spff
 
@@ -121,6 +143,19 @@ int spff_count_valid(const void* labels, int label_bytes, long long total, int i
     else
       spff::count_valid_kernel<long long><<<blocks, 256, 0, st>>>(static_cast<const long long*>(labels), total, ignore_index, out);
   }
+  SPFF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int spff_scale_by_count(float* g, long long n, const unsigned long long* count, float factor, void* stream) {
+  int e = spff_device_check();
+  if (e) return e;
+  SPFF_REQUIRE(g && count && n >= 0, "scale_by_count: bad arguments");
+  if (n == 0) return 0;
+  const long long b = (n / 4 + 255) / 256 + 1;
+  const int cap = spff::num_sms() * 8;
+  spff::scale_by_count_kernel<<<static_cast<int>(b < cap ? b : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, count,
+                                                                                                                  factor);
   SPFF_CUDA(cudaGetLastError());
   return 0;
 }

@@ -561,17 +561,22 @@ class BaseLitModel(pl.LightningModule):
                 if "ranges" not in st:
                     st["ranges"] = core.stage_ranges()
                 ranges = st["ranges"]
-                hook = lambda stage: pending.append(dp.allreduce_async(st["grad"][ranges[stage][0]:ranges[stage][1]]))
+                def hook(stage):
+                    g = st["grad"][ranges[stage][0]:ranges[stage][1]]
+                    ops.scale_by_count(g, st["tally"].n_valid)          # sum-CE gradients -> this rank's mean CE
+                    pending.append(dp.allreduce_async(g))
             core.engine.train_step(imgs, lbls, st["G"], st["tally"], group=group, ignore_index=IGNORE_INDEX,
                                    staged=staged, stage_done=hook)
             if pending:
                 ev = dp.exposed_timer_start()
                 lo, hi = ranges["tail"]
+                ops.scale_by_count(st["grad"][lo:hi], st["tally"].n_valid)
                 gscale = dp.allreduce_grads(st["grad"][lo:hi])
                 for w in pending:
                     w.wait()
                 dp.exposed_timer_stop(ev)
             else:
+                ops.scale_by_count(st["grad"], st["tally"].n_valid)      # the engine back-propagates the CE sum
                 gscale = dp.allreduce_grads(st["grad"])
             if optimize:
                 st["step"] += 1

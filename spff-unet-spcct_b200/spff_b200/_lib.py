@@ -86,6 +86,7 @@ _PROTOTYPES = {
     "spff_head_loss_fused": [_P, _LL, c_int, _P, _P, _P, c_int, c_int, c_int, Shape, _P, _P, _P, _P, _P, _P, _LL, _P, _P,
                              c_float, _P, c_size_t, _P],
     "spff_count_valid": [_P, c_int, _LL, c_int, _P, _P],
+    "spff_scale_by_count": [_P, _LL, _P, c_float, _P],
     "spff_loss_from_tally": [_P, _P, _P, c_int, c_double, _P, _P],
     "spff_partial_colsum_workspace": [c_int],
     "spff_partial_colsum": [_P, _LL, _LL, c_int, _P, _P, c_size_t, _P],

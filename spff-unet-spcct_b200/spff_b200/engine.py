@@ -280,6 +280,7 @@ class SpffEngine:
         self._packed_key = None
         self._bufs: Dict[tuple, _GroupBuffers] = {}
         self._fit: Dict[tuple, int] = {}
+        self._ones: Dict[str, torch.Tensor] = {}
 
     # ------------------------------------------------------------------------------------------
     def params(self) -> Dict[str, torch.Tensor]:
@@ -305,6 +306,12 @@ class SpffEngine:
 
     def invalidate_weights(self):
         self._packed_key = None
+
+    def _one(self, device) -> torch.Tensor:
+        t = self._ones.get(str(device))
+        if t is None:
+            t = self._ones[str(device)] = torch.ones(1, dtype=torch.int64, device=device)
+        return t
 
     def buffers(self, n, d, h, w, device, train: bool, fresh: bool = False) -> _GroupBuffers:
         if fresh:
@@ -598,11 +605,13 @@ class SpffEngine:
     def train_step(self, x: torch.Tensor, labels: torch.Tensor, G: Dict[str, torch.Tensor], tally: "LossTally",
                    group: int = 32, ignore_index: int = 255, staged: Optional["StagedBatch"] = None,
                    stage_done: Optional[Callable[[str], None]] = None):
-        """Fused forward + CE/confusion + backward over the batch in sample groups. Accumulates the
-        parameter gradients of the batch-mean CE (helpers.py:798-801; the Dice term of the loss has
-        no gradient, helpers.py:782-795) into G and the loss statistics into `tally`.
+        """Fused forward + CE/confusion + backward over the batch in sample groups. Accumulates into G the parameter
+        gradients of the SUM over valid voxels of the CE terms, and leaves the number of valid voxels in `tally.n_valid`:
+        the caller divides the finished gradients by it (ops.scale_by_count) to obtain the gradients of the batch-mean CE
+        (helpers.py:798-801; the Dice term of the loss has no gradient, helpers.py:782-795). Back-propagating the sum
+        keeps a group's backward independent of the other groups' labels. Loss statistics go into `tally`.
         `staged`: the batch is still arriving from pinned host memory on a copy stream (StagedBatch);
-        each group's forward waits only for its own slice.
+        each group waits only for its own images and labels.
         `stage_done(stage)`: called inside the LAST group's backward as soon as every gradient of a stage is final —
         "decoder" (head, decoder blocks, transposed convs), "bott", "enc3", "enc2", "enc1" — so that a data-parallel
         caller can start that range's all-reduce while the rest of the backward still runs."""
@@ -614,23 +623,22 @@ class SpffEngine:
         self.refresh_weights()
         group = self._fitted(min(group, bsz), d, h, w, x.device, train=True)
         T = GateTables(self.cfg, self.params(), d, need_grad=True)
-        n_valid = None
         p = self.params()
+        one = self._one(x.device)      # normaliser of the per-voxel CE gradient inside the step: 1 (sum reduction)
         for lo, hi in self._groups(bsz, group):
             if staged is not None:
                 staged.wait_images(hi)
             B = self.buffers(hi - lo, d, h, w, x.device, train=True)
             self.forward_group(B, T, x[lo:hi], head="none")
-            if n_valid is None:   # the CE normaliser spans the whole batch; first needed here
-                if staged is not None:
-                    staged.wait_labels()
-                n_valid = tally.n_valid
-                ops.count_valid(labels, ignore_index, n_valid)
+            if staged is not None:
+                staged.wait_labels(hi)
+            last = hi == bsz
+            if last:                   # every label is on the device: the CE normaliser of the whole batch
+                ops.count_valid(labels, ignore_index, tally.n_valid)
             # head + CE + confusion + their backward in one pass; the logits never reach memory
-            ops.head_loss_fused(B.out["dec1"], p["out.weight"], p["out.bias"], labels[lo:hi], ignore_index, n_valid, None,
+            ops.head_loss_fused(B.out["dec1"], p["out.weight"], p["out.bias"], labels[lo:hi], ignore_index, one, None,
                                 tally.nll, tally.count, tally.confusion, B.gout[1],
                                 G["out.weight"].view(-1, self.cfg.base), G["out.bias"], 1.0)
-            last = hi == bsz
             hook = None
             if last and stage_done is not None:
                 def hook(stage):
@@ -641,9 +649,9 @@ class SpffEngine:
 
 
 class StagedBatch:
-    """Host -> device staging of one batch on a dedicated copy stream: the first image group, then
-    the labels (needed early for N_valid), then the remaining image groups; the compute stream waits
-    per group, so the transfer of group g+1 overlaps the kernels of group g. Host tensors should be
+    """Host -> device staging of one batch on a dedicated copy stream, group by group: the images of a group, then its
+    labels. The compute stream waits per group (images before the forward, labels before the fused head / loss), so the
+    transfer of group g+1 overlaps the kernels of group g and nothing waits for the whole batch. Host tensors should be
     pinned (a pageable source still works, synchronously)."""
 
     def __init__(self, imgs: torch.Tensor, labels: torch.Tensor, device, group: int, stream: torch.cuda.Stream):
@@ -651,33 +659,33 @@ class StagedBatch:
         self.x = torch.empty(imgs.shape, dtype=torch.float32, device=device)
         self.labels = torch.empty(labels.shape, dtype=labels.dtype, device=device)
         self.h2d_bytes = imgs.numel() * 4 + labels.numel() * labels.element_size()
-        self._events = []       # (upper sample index, event)
+        self._events = []       # (upper sample index, images there, labels there)
         stream.wait_stream(torch.cuda.current_stream(device))
         src = imgs if imgs.dtype == torch.float32 else imgs.float()
         with torch.cuda.stream(stream):
-            first = True
             for lo in range(0, bsz, max(1, group)):
                 hi = min(bsz, lo + group)
                 self.x[lo:hi].copy_(src[lo:hi], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
-                self._events.append((hi, ev))
-                if first:
-                    self.labels.copy_(labels, non_blocking=True)
-                    self._labels_ev = torch.cuda.Event()
-                    self._labels_ev.record(stream)
-                    first = False
+                self.labels[lo:hi].copy_(labels[lo:hi], non_blocking=True)
+                evl = torch.cuda.Event()
+                evl.record(stream)
+                self._events.append((hi, ev, evl))
         self.x.record_stream(stream)
         self.labels.record_stream(stream)
 
-    def wait_labels(self):
-        torch.cuda.current_stream().wait_event(self._labels_ev)
+    def _wait(self, upto: int, which: int):
+        for rec in self._events:
+            if rec[0] >= upto:
+                torch.cuda.current_stream().wait_event(rec[which])
+                return
 
     def wait_images(self, upto: int):
-        for hi, ev in self._events:
-            if hi >= upto:
-                torch.cuda.current_stream().wait_event(ev)
-                return
+        self._wait(upto, 1)
+
+    def wait_labels(self, upto: int):
+        self._wait(upto, 2)
 
 
 class LossTally:

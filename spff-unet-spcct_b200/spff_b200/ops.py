@@ -361,6 +361,12 @@ def head_loss_fused(x, w, b, labels, ignore_index, n_valid, gscale, acc, counts,
          ptr(ws), ws.numel(), stream_ptr())
 
 
+def scale_by_count(g, count, factor: float = 1.0):
+    """g (fp32, contiguous) *= factor / count[0]  (0 when the count is 0)."""
+    assert g.dtype == torch.float32 and g.is_contiguous() and count.dtype == torch.int64
+    call("spff_scale_by_count", ptr(g), g.numel(), ptr(count), float(factor), stream_ptr())
+
+
 def count_valid(labels, ignore_index, out):
     """out (int64 [1]) = number of labels != ignore_index."""
     call("spff_count_valid", ptr(labels), _label_bytes(labels), labels.numel(), int(ignore_index), ptr(out), stream_ptr())

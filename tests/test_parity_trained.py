@@ -181,7 +181,10 @@ def test_per_layer_activation_gradients(gpu_run):
     z, lit, logits, out, B, lab = gpu_run
     y = np.load(YARD)
     yard = dict(zip([str(n) for n in y["yard_names"]], y["yard_vals"]))
-    nchw = lambda t: t.permute(0, 4, 1, 2, 3).float()
+    # the fused step back-propagates the SUM of the CE terms and divides the finished parameter gradients by N_valid
+    # (engine.train_step); the activation gradients in its buffers therefore carry the factor N_valid
+    inv_n = 1.0 / float(out["tally"].n_valid.item())
+    nchw = lambda t: t.permute(0, 4, 1, 2, 3).float() * inv_n
     got = {"dec1": B.gout[1], "dec2": B.gout[2], "dec3": B.gout[3], "bott": B.gout[4]}
     for l, e in ((1, "enc1"), (2, "enc2"), (3, "enc3")):
         got[e] = B.dcat[l][..., B.C[l]:]
