@@ -32,6 +32,10 @@ def main():
     if len(sys.argv) > 3 and sys.argv[3] == "rows":      # force the flattened-row kernel of conv3_fprop.cu (debug key 7)
         from spff_b200 import _lib
         _lib.lib.spff_debug_set(7, 1)
+    if len(sys.argv) > 3 and sys.argv[3].startswith("key"):      # keyK=V: spff_debug_set(K, V)
+        from spff_b200 import _lib
+        k, v = sys.argv[3][3:].split("=")
+        _lib.lib.spff_debug_set(int(k), int(v))
     if len(sys.argv) > 3 and sys.argv[3].startswith("dbg"):
         from spff_b200 import _lib
         _lib.lib.spff_debug_set(5, int(sys.argv[3][3:]))

@@ -35,6 +35,7 @@ struct WgradParams {
   int G, ngroups;
   int ncob, ncib;    // channel blocks
   int ksplit;
+  int halo_w;        // all-kh variant: 1 = ONE x tile with a w halo serves the three kw shifts (bw == 8)
   float* partial;    // [item][split][mma][128][3*CIB]
 };
 
@@ -284,14 +285,17 @@ __global__ void conv3_wgrad_reduce_kernel(const float* __restrict__ partial, flo
 // ---------------------------------------------------------------------------------------------
 // 32 x 32 channel-block variant with all three kh taps in one CTA. With few channels the kernel above
 // is bound by L2 -> SM traffic (ncu: 11.8 TB/s for 32 -> 32: every operand byte crosses 3 x for the kh
-// work items, x another 3 x for the kw-shifted tiles). Here the x tile carries a one-row halo above and
-// below ((bh + 2) x bw positions), so the kh-shifted operand is the same tile read at a row offset of
-// kh * bw (a multiple of the 8-row swizzle atom) and dy is loaded once for all nine (kh, kw) taps of a
-// plane. Accumulators: 3 (kh) x [128 x 96] fp32 = 288 TMEM columns. Work item = (cob, cib, split).
+// work items, x another 3 x for the kw-shifted tiles). Here ONE x tile with a halo in h and w
+// ((bh + 2) x (bw + 2) positions, bw = 8) serves all nine (kh, kw) taps of a plane: the kh-shifted operand
+// is the tile read from row kh * (bw + 2), the three kw-shifted 32-channel blocks of N start one row
+// (64 bytes) apart (LBO), and the 8-row K groups are the tile's image rows, bw + 2 rows apart (SBO) - the
+// tensor core swizzles on the absolute address, so none of these offsets needs atom alignment. dy is
+// loaded once per plane. (Round 2 before this: three separately loaded kw tiles, 3 % slower; debug key 9.)
+// Accumulators: 3 (kh) x [128 x 96] fp32 = 288 TMEM columns. Work item = (cob, cib, split).
 // ---------------------------------------------------------------------------------------------
 struct WgKhCfg {
   static constexpr int COB = 32, CIB = 32, N = 96;
-  static constexpr int XTMax = 160 * CIB * 2;            // (bh + 2) * bw <= 160 rows of 64 B
+  static constexpr int XTMax = 160 * CIB * 2;            // (bh + 2) * bw <= 160 rows of 64 B; halo_w: ONE tile of (bh + 2) * (bw + 2) <= 180 rows per stage
   static constexpr int XBytes = 3 * XTMax;               // three kw tiles
   static constexpr int XStages = 3;
   static constexpr int DySet = kSlots * kSlotBytes;
@@ -354,7 +358,8 @@ conv3_wgrad_kh_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
   const long long t_begin = p.ntiles * split / p.ksplit;
   const long long t_end = p.ntiles * (split + 1) / p.ksplit;
   const int rows = p.bw * p.bh;                    // dy tile rows (K)
-  const int xrows = p.bw * (p.bh + 2);             // x tile rows incl. the halo
+  const int xpitch = p.halo_w ? p.bw + 2 : p.bw;   // positions per image row of the x tile
+  const int xrows = xpitch * (p.bh + 2);           // x tile rows incl. the halo
   const uint32_t dy_tile_bytes = rows * C::COB * 2;
   const uint32_t x_tile_bytes = xrows * C::CIB * 2;
 
@@ -383,10 +388,15 @@ conv3_wgrad_kh_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
         for (int dp = d0; dp < dend; ++dp) {
           mbar_wait(&xempty[xs], xph ^ 1);
           if (leader) {
-            mbar_expect_tx(&xfull[xs], 3 * x_tile_bytes);
+            if (p.halo_w) {
+              mbar_expect_tx(&xfull[xs], x_tile_bytes);
+              tma_load_5d(sX + xs * C::XBytes, &tmap_x, &xfull[xs], cib * C::CIB, w0 - 1, h0 - 1, dp, n);
+            } else {
+              mbar_expect_tx(&xfull[xs], 3 * x_tile_bytes);
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-              tma_load_5d(sX + xs * C::XBytes + kw * C::XTMax, &tmap_x, &xfull[xs], cib * C::CIB, w0 + kw - 1, h0 - 1, dp, n);
+              for (int kw = 0; kw < 3; ++kw)
+                tma_load_5d(sX + xs * C::XBytes + kw * C::XTMax, &tmap_x, &xfull[xs], cib * C::CIB, w0 + kw - 1, h0 - 1, dp, n);
+            }
           }
           if (++xs == C::XStages) {
             xs = 0;
@@ -399,12 +409,17 @@ conv3_wgrad_kh_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
     const bool leader = elect_one() != 0;
     // MN-major operands: LBO = stride between 32-channel blocks (dy: next plane slot; x: next kw tile), SBO = 8 K rows
     const uint64_t adesc_hi = make_smem_desc_hi(kSlotBytes, 512, kSwizzle64);
-    const uint64_t bdesc_hi = make_smem_desc_hi(C::XTMax, 512, kSwizzle64);
+    // halo_w: the tensor core applies the swizzle to the absolute shared-memory address (scripts/micro/umma_rowshift.cu), so
+    // the three kw-shifted operands are the SAME tile read one row (= one position) apart - the three 32-channel blocks
+    // of N start 64 bytes from each other (LBO) - and an 8-row K group is one image row of the tile: SBO = bw + 2 rows.
+    const uint32_t sbo_b = p.halo_w ? static_cast<uint32_t>(xpitch * C::CIB * 2) : 512u;
+    const uint64_t bdesc_hi = make_smem_desc_hi(p.halo_w ? C::CIB * 2 : C::XTMax, sbo_b, kSwizzle64);
     const uint32_t idesc = make_idesc_bf16(128, C::N, 1, 1);
     const uint64_t adesc0 = smem_desc(adesc_hi, smem_u32(sDy));
     const uint64_t bdesc0 = smem_desc(bdesc_hi, smem_u32(sX));
     const int ksteps = rows / 16;
-    const uint32_t kh_step = static_cast<uint32_t>(p.bw * C::CIB * 2) >> 4;   // one image row of the x tile
+    const uint32_t kh_step = static_cast<uint32_t>(xpitch * C::CIB * 2) >> 4;   // one image row of the x tile
+    const uint32_t b_step = (2 * sbo_b) >> 4;                                   // 16 K rows
     int xs = 0, ds = 0;
     uint32_t xph = 0, dph = 0;
     uint32_t first = 1;
@@ -427,7 +442,7 @@ conv3_wgrad_kh_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_
             for (int ks = 0; ks < ksteps; ++ks) {
               if (leader) umma_bf16(tmem_base + kh * C::N, ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
               ad += (2 * 512) >> 4;
-              bd += (2 * 512) >> 4;
+              bd += b_step;
             }
           }
           first = 0;
@@ -511,7 +526,7 @@ WgPlan make_plan(int cin, int cout, spff_shape s) {
   if ((cin == 32 || cout == 32) && s.w % 8 == 0 && debug_flag(1) == 0) {
     pl.allkh = 1;
     pl.cob = pl.cib = 32;
-    pl.bw = s.w < 16 ? s.w : 16;
+    pl.bw = (debug_flag(9) == 0) ? 8 : (s.w < 16 ? s.w : 16);   // 8: one x tile with a w halo serves the three kw shifts (key 9: the three-tile form)
     int bh = 128 / pl.bw;
     if (bh > s.h) bh = s.h;
     while ((pl.bw * bh) % 16) ++bh;   // K steps of 16 rows (rows past H are zero filled)
@@ -578,6 +593,7 @@ int launch_wgrad(const void* x, long long ldx, int cin, const void* dy, long lon
   p.n = s.n; p.d = s.d; p.h = s.h; p.w = s.w;
   p.bw = pl.bw; p.bh = pl.bh; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.ntiles = pl.ntiles;
   p.G = pl.G; p.ngroups = pl.ngroups; p.ncob = pl.ncob; p.ncib = pl.ncib; p.ksplit = pl.ksplit;
+  p.halo_w = 0;
   p.partial = partial;
   CUtensorMap tdy, tx;
   {
@@ -619,6 +635,7 @@ int launch_wgrad_kh(const void* x, long long ldx, int cin, const void* dy, long 
   p.bw = pl.bw; p.bh = pl.bh; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.ntiles = pl.ntiles;
   p.G = pl.G; p.ngroups = pl.ngroups; p.ncob = pl.ncob; p.ncib = pl.ncib; p.ksplit = pl.ksplit;
   p.partial = partial;
+  p.halo_w = (pl.bw == 8) ? 1 : 0;
   CUtensorMap tdy, tx;
   {
     uint64_t dims[5] = {static_cast<uint64_t>(cout), static_cast<uint64_t>(s.w), static_cast<uint64_t>(s.h),
@@ -634,7 +651,7 @@ int launch_wgrad_kh(const void* x, long long ldx, int cin, const void* dy, long 
                         static_cast<uint64_t>(s.d), static_cast<uint64_t>(s.n)};
     uint64_t str[4] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(ldx) * 2 * s.w,
                        static_cast<uint64_t>(ldx) * 2 * s.w * s.h, static_cast<uint64_t>(ldx) * 2 * s.w * s.h * s.d};
-    uint32_t box[5] = {32, static_cast<uint32_t>(pl.bw), static_cast<uint32_t>(pl.bh + 2), 1, 1};
+    uint32_t box[5] = {32, static_cast<uint32_t>(pl.bw + (p.halo_w ? 2 : 0)), static_cast<uint32_t>(pl.bh + 2), 1, 1};
     int e = encode_tmap_bf16(&tx, x, 5, dims, str, box, 64);
     if (e) return e;
   }

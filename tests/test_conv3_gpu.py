@@ -168,6 +168,27 @@ def test_conv3_wgrad(n, d, h, w, cin, cout):
     assert ((dw - 2 * ref).norm() / ref.norm()) < 2e-4
 
 
+@pytest.mark.parametrize("n,d,h,w,cin,cout", [(2, 5, 16, 16, 32, 32), (1, 5, 8, 24, 32, 32), (2, 5, 128, 128, 64, 32)])
+def test_conv3_wgrad_three_tile_form(n, d, h, w, cin, cout):
+    """The 32-channel weight-gradient kernel reads the three kw-shifted x operands from ONE halo tile (blocks of N one row
+    apart); debug key 9 selects the earlier form with three separately loaded tiles — same result to fp32 summation order."""
+    from spff_b200 import _lib, ops
+    x = _mk(n, cin, d, h, w, 17)
+    dy = _mk(n, cout, d, h, w, 18)
+    xb, dyb = _to_ndhwc_bf16(x), _to_ndhwc_bf16(dy)
+    dw = torch.full((cout, cin, 3, 3, 3), float("nan"), device="cuda")
+    ops.conv3d_k3_wgrad(xb, cin, dyb, cout, dw, 0.0)
+    _lib.lib.spff_debug_set(9, 1)
+    try:
+        dw3 = torch.full_like(dw, float("nan"))
+        ops.conv3d_k3_wgrad(xb, cin, dyb, cout, dw3, 0.0)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib.spff_debug_set(9, 0)
+    assert torch.isfinite(dw3).all()
+    assert ((dw - dw3).norm() / dw3.norm()) < 1e-5
+
+
 @pytest.mark.parametrize("n,d,h,w,cin,cout", CASES)
 def test_conv3_fwd_with_fused_statistics(n, d, h, w, cin, cout, conv_kernel):
     """spff_conv3d_k3_fwd_stats: same output as the plain forward (bit-exact) and InstanceNorm
