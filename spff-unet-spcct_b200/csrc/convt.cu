@@ -51,7 +51,8 @@ struct PwSmem {
   static constexpr int kOffBar = kStages * kStage;
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
-  static constexpr int kTotal = kOffTmem + 16;
+  static constexpr int kOffBias = kOffTmem + 16;          // fp32 bias of the launch's N <= 256 output channels
+  static constexpr int kTotal = kOffBias + 256 * 4;
 };
 
 template <int KC>
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
   uint64_t* acc_full = bars + 2 * L::kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kOffTmem);
+  float* sbias = reinterpret_cast<float*>(smem + L::kOffBias);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
     }
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < p.N; i += kThreads) sbias[i] = p.bias ? __ldg(p.bias + p.noff + i) : 0.f;
   if (warp == 4 && lane == 0) {
     for (int t = 0; t < p.ntap; ++t) tma_prefetch_desc(&maps.a[t]);
     tma_prefetch_desc(&maps.b);
@@ -201,13 +204,10 @@ __global__ void __launch_bounds__(kThreads, 1) pw_gemm_kernel(const __grid_const
           if (ok) {
             uint32_t pk[16];
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              float a = __uint_as_float(v[c]), b = __uint_as_float(v[c + 1]);
-              if (p.bias) {
-                a += __ldg(p.bias + p.noff + c0 + c);
-                b += __ldg(p.bias + p.noff + c0 + c + 1);
-              }
-              pk[c >> 1] = pack_bf16x2(a, b);
+            for (int c = 0; c < 32; c += 4) {      // bias: one broadcast 16-byte shared load per 4 channels
+              const float4 bv = *reinterpret_cast<const float4*>(sbias + c0 + c);
+              pk[c >> 1] = pack_bf16x2(__uint_as_float(v[c]) + bv.x, __uint_as_float(v[c + 1]) + bv.y);
+              pk[(c >> 1) + 1] = pack_bf16x2(__uint_as_float(v[c + 2]) + bv.z, __uint_as_float(v[c + 3]) + bv.w);
             }
             if ((p.ldo & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0) {   // 32-byte aligned rows: full-sector stores
               st_global_v8(dst + c0, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
