@@ -221,9 +221,10 @@ stem_fwd_stats_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 // ---------------------------------------------------------------------------------------------
 constexpr int kSfWarps = 8;
 constexpr int kSfSeg = 128;                  // positions per segment
-constexpr int kSfPitch = kSfSeg + 2 + 6;     // bf16 per window row
+constexpr int kSfPitch = kSfSeg + 8;         // window elements per row; column c of the window sits at index c + 3, so that the
+                                             // 128 core columns start 16-byte aligned
 constexpr int kSfOutPitch = 40;              // bf16 per staged output row (32 + 8 pad: conflict-free)
-constexpr int kSfSmemBytes = (kSfWarps * 2 * 9 * kSfPitch + kSfWarps * 16 * kSfOutPitch) * 2;
+constexpr int kSfSmemBytes = kSfWarps * 9 * kSfPitch * 4 + kSfWarps * 16 * kSfOutPitch * 2;
 
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16(v);
@@ -231,6 +232,12 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 }
 __device__ __forceinline__ uint32_t pack_u16(const __nv_bfloat16 a, const __nv_bfloat16 b) {
   return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+// one window element: bf16 head in the low half, bf16 remainder in the high half
+__device__ __forceinline__ uint32_t split_packed(float v) {
+  __nv_bfloat16 hi, lo;
+  split_bf16(v, hi, lo);
+  return pack_u16(hi, lo);
 }
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -242,12 +249,11 @@ __global__ void __launch_bounds__(kSfWarps * 32, 2)
 stem_fwd_stats_mma_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
                           long long ldy, spff_shape s, float* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char sf_smem[];
-  __nv_bfloat16* xs_all = reinterpret_cast<__nv_bfloat16*>(sf_smem);           // [warp][hi/lo][9][kSfPitch]
-  __nv_bfloat16* os_all = xs_all + kSfWarps * 2 * 9 * kSfPitch;                // [warp][16][kSfOutPitch]
+  uint32_t* xs_all = reinterpret_cast<uint32_t*>(sf_smem);                     // [warp][9][kSfPitch] (hi | lo << 16)
+  __nv_bfloat16* os_all = reinterpret_cast<__nv_bfloat16*>(xs_all + kSfWarps * 9 * kSfPitch);   // [warp][16][kSfOutPitch]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  __nv_bfloat16* xh = xs_all + warp * 2 * 9 * kSfPitch;
-  __nv_bfloat16* xl = xh + 9 * kSfPitch;
+  uint32_t* xw = xs_all + warp * 9 * kSfPitch;
   __nv_bfloat16* os = os_all + warp * 16 * kSfOutPitch;
   // B fragments (K = tap, N = channel), constant for the whole launch; taps >= 27 carry zero weights, so the A
   // values gathered for them do not matter
@@ -261,7 +267,7 @@ stem_fwd_stats_mma_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int k = k0 + e;
-        toff[ks][j][e] = k < 27 ? (k / 3) * kSfPitch + k % 3 : 0;
+        toff[ks][j][e] = k < 27 ? (k / 3) * kSfPitch + k % 3 + 3 : 3;
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
@@ -279,6 +285,7 @@ stem_fwd_stats_mma_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) ssum[nt][0] = ssum[nt][1] = ssq[nt][0] = ssq[nt][1] = 0.f;
   const bool wide = ((ldy & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 31) == 0);
+  const bool xvec = (s.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);   // 16-byte loads of the window rows
   const int segs = (s.w + kSfSeg - 1) / kSfSeg;
   const int nwork = s.d * s.h * segs;                         // of this sample
   const long long row0 = static_cast<long long>(blockIdx.y) * s.d * s.h;
@@ -290,19 +297,30 @@ stem_fwd_stats_mma_kernel(const float* __restrict__ x, const float* __restrict__
     const int w0 = sg * kSfSeg;
     const int wn = min(kSfSeg, s.w - w0);
     const int wpad = (wn + 15) & ~15;
-    // input window, split: xh/xl[kd*3+kh][c] = x[dd+kd-1][hh+kh-1][w0 + c - 1]
+    // input window, split: xw[kd*3+kh][c + 3] = x[dd+kd-1][hh+kh-1][w0 + c - 1]
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const int d2 = dd + r / 3 - 1, h2 = hh + r % 3 - 1;
       const bool rok = d2 >= 0 && d2 < s.d && h2 >= 0 && h2 < s.h;
-      const float* xr = x + (row + static_cast<long long>(r / 3 - 1) * s.h + (r % 3 - 1)) * s.w + w0 - 1;
-      for (int c = lane; c < wpad + 2; c += 32) {
-        const int w2 = w0 + c - 1;
-        const float v = (rok && w2 >= 0 && w2 < s.w) ? __ldg(xr + c) : 0.f;
-        __nv_bfloat16 hi, lo;
-        split_bf16(v, hi, lo);
-        xh[r * kSfPitch + c] = hi;
-        xl[r * kSfPitch + c] = lo;
+      const float* xr = x + (row + static_cast<long long>(r / 3 - 1) * s.h + (r % 3 - 1)) * s.w + w0;   // column 1 of the window
+      uint32_t* dst = xw + r * kSfPitch;
+      if (xvec) {
+        // every lane: 4 core columns (one 16-byte load, one 16-byte store); lanes 0 / 1: the left / right halo column
+        const int c4 = 4 * lane;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rok && w0 + c4 < s.w) v = __ldg(reinterpret_cast<const float4*>(xr + c4));
+        *reinterpret_cast<uint4*>(dst + 4 + c4) = make_uint4(split_packed(v.x), split_packed(v.y), split_packed(v.z), split_packed(v.w));
+        if (lane < 2) {
+          const int w2 = lane == 0 ? w0 - 1 : w0 + kSfSeg;
+          const float hv = (rok && w2 >= 0 && w2 < s.w) ? __ldg(xr + (w2 - w0)) : 0.f;
+          dst[lane == 0 ? 3 : 4 + kSfSeg] = split_packed(hv);
+        }
+      } else {
+        for (int c = lane; c < wpad + 2; c += 32) {
+          const int w2 = w0 + c - 1;
+          const float v = (rok && w2 >= 0 && w2 < s.w) ? __ldg(xr + c - 1) : 0.f;
+          dst[c + 3] = split_packed(v);
+        }
       }
     }
     __syncwarp();
@@ -316,9 +334,9 @@ stem_fwd_stats_mma_kernel(const float* __restrict__ x, const float* __restrict__
         for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int rh = 0; rh < 2; ++rh) {
-            const int e0 = toff[ks][j][0] + p + 8 * rh, e1 = toff[ks][j][1] + p + 8 * rh;
-            ah[ks][2 * j + rh] = pack_u16(xh[e0], xh[e1]);
-            al[ks][2 * j + rh] = pack_u16(xl[e0], xl[e1]);
+            const uint32_t u0 = xw[toff[ks][j][0] + p + 8 * rh], u1 = xw[toff[ks][j][1] + p + 8 * rh];
+            ah[ks][2 * j + rh] = __byte_perm(u0, u1, 0x5410);     // the two heads
+            al[ks][2 * j + rh] = __byte_perm(u0, u1, 0x7632);     // the two remainders
           }
       float acc[4][4];
 #pragma unroll
