@@ -428,7 +428,8 @@ stem_fwd_stats_mma_kernel(const float* __restrict__ x, const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 constexpr int kSwgWarps = 8;
 constexpr int kSwgSeg = 128;                 // positions per segment
-constexpr int kSwgWin = kSwgSeg + 2 + 2;     // window columns (+2 halo, +2 so that 32-bit pair loads stay inside)
+constexpr int kSwgWin = kSwgSeg + 8;         // window row: column c at index c + 3 (the 128 core columns start 8-byte aligned), +2 halo,
+                                             // + slack so that the 32-bit pair loads stay inside
 constexpr int kSwgDyPitch = 40;              // bf16 per staged dy row (32 + 8 pad: conflict-free ldmatrix)
 constexpr int kSwgBlocksPerSm = 2;
 
@@ -455,10 +456,11 @@ stem_wgrad_mma_kernel(const float* __restrict__ x, const __nv_bfloat16* __restri
     const int tap = g + 8 * i;
     tok[i] = tap < 27;
     const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-    toff[i] = tok[i] ? (kd * 3 + kh) * kSwgWin + kw : 0;
+    toff[i] = tok[i] ? (kd * 3 + kh) * kSwgWin + kw + 3 : 0;
   }
   const int segs = (s.w + kSwgSeg - 1) / kSwgSeg;
   const long long nwork = static_cast<long long>(s.n) * s.d * s.h * segs;
+  const bool xvec = (s.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);   // 16-byte loads of the window rows
   const __nv_bfloat16* xw = &xs[warp][0][0];
   const uint32_t* xw32 = reinterpret_cast<const uint32_t*>(xw);
   for (long long work = static_cast<long long>(blockIdx.x) * kSwgWarps + warp; work < nwork;
@@ -470,16 +472,30 @@ stem_wgrad_mma_kernel(const float* __restrict__ x, const __nv_bfloat16* __restri
     const int w0 = sg * kSwgSeg;
     const int wn = min(kSwgSeg, s.w - w0);                    // valid positions of this segment
     const int wpad = (wn + 15) & ~15;
-    // input window: xs[kd*3+kh][c] = x[dd+kd-1][hh+kh-1][w0 + c - 1]
+    // input window: xs[kd*3+kh][c + 3] = x[dd+kd-1][hh+kh-1][w0 + c - 1]
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const int d2 = dd + r / 3 - 1, h2 = hh + r % 3 - 1;
       const bool rok = d2 >= 0 && d2 < s.d && h2 >= 0 && h2 < s.h;
-      const float* xr = x + (row + static_cast<long long>(r / 3 - 1) * s.h + (r % 3 - 1)) * s.w + w0 - 1;
-      for (int c = lane; c < wpad + 2; c += 32) {
-        const int w2 = w0 + c - 1;
-        const float v = (rok && w2 >= 0 && w2 < s.w) ? __ldg(xr + c) : 0.f;
-        xs[warp][r][c] = __float2bfloat16(v);
+      const float* xr = x + (row + static_cast<long long>(r / 3 - 1) * s.h + (r % 3 - 1)) * s.w + w0;   // window column 1
+      __nv_bfloat16* dst = &xs[warp][r][0];
+      if (xvec) {
+        // every lane: 4 core columns (one 16-byte load, one 8-byte store); lanes 0 / 1: the left / right halo column
+        const int c4 = 4 * lane;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rok && w0 + c4 < s.w) v = __ldg(reinterpret_cast<const float4*>(xr + c4));
+        *reinterpret_cast<uint2*>(dst + 4 + c4) = make_uint2(pack_bf16x2_local(v.x, v.y), pack_bf16x2_local(v.z, v.w));
+        if (lane < 2) {
+          const int w2 = lane == 0 ? w0 - 1 : w0 + kSwgSeg;
+          const float hv = (rok && w2 >= 0 && w2 < s.w) ? __ldg(xr + (w2 - w0)) : 0.f;
+          dst[lane == 0 ? 3 : 4 + kSwgSeg] = __float2bfloat16(hv);
+        }
+      } else {
+        for (int c = lane; c < wpad + 2; c += 32) {
+          const int w2 = w0 + c - 1;
+          const float v = (rok && w2 >= 0 && w2 < s.w) ? __ldg(xr + c - 1) : 0.f;
+          dst[c + 3] = __float2bfloat16(v);
+        }
       }
     }
     __syncwarp();
