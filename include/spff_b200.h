@@ -51,9 +51,17 @@ int spff_version(void);
 const char* spff_last_error(void);
 /* 0 when the current CUDA device is sm_100 (B200); SPFF_ERR_UNSUPPORTED_ARCH otherwise. */
 int spff_device_check(void);
-/* test hook. key 0: number of CTAs for persistent kernels (0 = one per SM); key 1: non-zero disables the
- * all-kh variant of the 32-channel weight-gradient kernel; key 2: non-zero selects the CUDA-core fused head kernel
- * instead of the mma.sync one. */
+/* Test / measurement hook (never needed in production; 0 = default everywhere). Keys:
+ *   0  number of CTAs for the persistent kernels (0 = one per SM)
+ *   1  non-zero disables the all-kh variant of the 32-channel weight-gradient kernel
+ *   2  non-zero selects the CUDA-core fused head kernel instead of the mma.sync one
+ *   3, 4  blocks per SM of the InstanceNorm statistics / backward statistics kernels
+ *   4  (conv kernels) device pointer of a cycle-counter buffer; 5  timing experiments of the halo conv kernel and, in the
+ *      transposed conv, no quadrant folding
+ *   6  non-zero disables the aligned epilogue of the flattened-row conv kernel
+ *   7  1 = always the flattened-row conv kernel, 2 = always the halo-tile kernel
+ *   8  non-zero selects the fp32 FMA stem forward instead of the mma.sync one
+ *   9  non-zero: the 32-channel weight gradient loads three kw-shifted x tiles instead of one halo tile */
 int spff_debug_set(int key, long long value);
 
 /* ---- 3x3x3 convolution, stride 1, zero pad 1, no bias ----------------------------------------
